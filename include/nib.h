@@ -1,0 +1,273 @@
+/*
+ * nib.h — C ABI of libnib.so, the B200 (sm_100a) engine for the perturbation-interpretation
+ * hot path of LiliMeng/network_interpretation_imagenet:
+ *
+ *     mask synthesis  ->  classifier scoring  ->  Gaussian-process surrogate + acquisition
+ *
+ * The reference has no FFI of its own (it is flat Python); every entry point
+ * below names the reference call site (file:line under the reference tree) whose arithmetic
+ * it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (NIB_OK) or a negative NIB_E* code; nib_last_error() gives the
+ *     text of the most recent failure on the calling thread.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (torch tensors in practice);
+ *     pointers named h_* are HOST pointers, read during the call only.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     NIB_ENODEVICE.
+ *   - handles are not thread-safe; one handle per rank/process.
+ */
+#ifndef NIB_H_
+#define NIB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIB_ABI_VERSION 1
+
+enum nib_status {
+  NIB_OK = 0,
+  NIB_EINVAL = -1,      /* bad argument (shape, alignment, enum)            */
+  NIB_ECUDA = -2,       /* a CUDA runtime/driver call failed                */
+  NIB_ENODEVICE = -3,   /* no CUDA device / not an sm_100 part              */
+  NIB_ENOMEM = -4,      /* device allocation failed                         */
+  NIB_ESTATE = -5,      /* handle used in the wrong state                   */
+  NIB_ENUMERIC = -6     /* numerical failure (Cholesky pivot <= 0)          */
+};
+
+int nib_abi_version(void);
+const char* nib_last_error(void);
+/* device_count<0 on error; sets *sm_major/*sm_minor/*num_sms of device `dev` when non-NULL */
+int nib_device_info(int dev, int* sm_major, int* sm_minor, int* num_sms);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1 — mask synthesis
+ * ---------------------------------------------------------------------------------------- */
+
+/* How a selection bit-vector z in {0,1}^S turns a label map into a classifier input. */
+enum nib_mask_mode {
+  /* generate_gp_training_data_imagenet.py:234-240, bayesian_active_learning_imagenet.py:182-187
+   * mask[p] = z[label[p]] (uint8 0/1);  out = x * (float)mask   — signed zeros preserved. */
+  NIB_MASK_KEEP_MUL = 0,
+  /* generate_gp_training_data_mnist.py:218-242, generate_gp_training_data_cifar.py:310-321
+   * mask[p] = z[label[p]] ? 0 : 255;  m = org*mask; m -= min(m); m /= max(m); m *= 255;
+   * out = m * float32(1/255)  (utils.py:92-94) — all fp32, this operation order. */
+  NIB_MASK_REMOVE_MINMAX = 1
+};
+
+enum nib_dtype { NIB_F32 = 0, NIB_BF16 = 1 };
+
+/* Output placement.  NCHW: out[n][c][h][w] (the reference's layout, C channels exactly).
+ * NHWC: out[n][h+pad_h][w+pad_w][c], row pitch (W+2*pad_w)*c_stride, channels c>=C and the
+ * pad_h/pad_w halo are written as +0 (the conv path wants a zero halo and padded channels). */
+enum nib_layout { NIB_NCHW = 0, NIB_NHWC = 1 };
+
+typedef struct nib_mask_args {
+  const float* d_img;        /* [C,H,W] fp32: normalised image (KEEP_MUL) or the [0,255]-rescaled
+                                image `org_img` (REMOVE_MINMAX, mnist :169-177)                    */
+  const void* d_labels;      /* [H,W] superpixel labels 0..S-1, uint8 (label_bytes=1) or uint16   */
+  int label_bytes;
+  const uint64_t* d_sel;     /* [N, sel_words] selection bit-vectors, bit s of word s/64 = z[s]   */
+  int sel_words;
+  int N, C, H, W, S;
+  int mode;                  /* nib_mask_mode */
+  const float* d_seg_minmax; /* [S,2] per-segment (min,max) of d_img over all channels; required
+                                for REMOVE_MINMAX (see nib_segment_minmax), ignored otherwise     */
+  void* d_out;
+  int out_dtype;             /* nib_dtype */
+  int layout;                /* nib_layout */
+  int c_stride;              /* NHWC only: channels per pixel in memory (>= C)                    */
+  int pad_h, pad_w;          /* NHWC only: zero halo                                              */
+  uint8_t* d_pixel_mask;     /* optional [N,H,W] uint8 pixel masks exactly as the reference holds
+                                them (0/1 KEEP_MUL, 0/255 REMOVE_MINMAX) — the PNG payload of
+                                imagenet :260/:265; NULL to skip                                   */
+} nib_mask_args;
+
+/* Per-segment (min,max) of a [C,H,W] fp32 image over all channels -> d_seg_minmax[S][2].
+ * Replaces the two global reductions of mnist :228-231 / cifar :318-319 for every mask at once. */
+int nib_segment_minmax(const float* d_img, const void* d_labels, int label_bytes,
+                       int C, int H, int W, int S, float* d_seg_minmax, void* stream);
+
+int nib_mask_synth(const nib_mask_args* args, void* stream);
+
+/* In-place per-image min-max rescale to [0,255] and the truncated uint8 HWC view (a1):
+ * mnist :169-177, cifar :275-283, imagenet :171-178.   d_org [C,H,W] fp32 (overwritten),
+ * d_u8 [H,W,C] uint8 (may be NULL). */
+int nib_prep_minmax_u8(float* d_org, int C, int H, int W, uint8_t* d_u8, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2 — classifier forward (models/resnet.py, models/densenet.py, mnist :86-105,
+ * torchvision resnet101/densenet121 via imagenet :579) and scoring
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct nib_net nib_net;
+
+enum nib_precision {
+  NIB_PREC_FP32 = 0,  /* fp32 activations/weights, SIMT kernels: the 1e-4 parity mode         */
+  NIB_PREC_BF16 = 1   /* bf16 activations/weights, fp32 accumulate, tcgen05 implicit GEMM     */
+};
+
+/* A network is a flat list of ops over numbered activation buffers (NHWC, per-image geometry
+ * H x W x C).  The host mirror (network_interpretation_imagenet_b200/classifier.py) walks the
+ * reference's nn.Module and emits this list with BatchNorm folded. */
+int nib_net_create(int precision, int max_batch, nib_net** out);
+int nib_net_destroy(nib_net* net);
+
+/* returns buffer id >= 0.  pad = zero halo kept around H and W (0 for all but the stem input) */
+int nib_net_add_buffer(nib_net* net, int H, int W, int C, int pad);
+
+enum nib_conv_flags {
+  NIB_CONV_RELU = 1,         /* ReLU after bias (+residual)                                    */
+  NIB_CONV_PRE_BNRELU = 2    /* DenseNet pre-activation: x <- relu(x*pre_scale+pre_shift) on the
+                                conv INPUT, per input channel (models/densenet.py:16-27)         */
+};
+
+typedef struct nib_conv_desc {
+  int in_buf, in_coff, Cin;       /* input = channels [in_coff, in_coff+Cin) of in_buf           */
+  int out_buf, out_coff, Cout;    /* output written to channels [out_coff, out_coff+Cout)        */
+  int res_buf, res_coff, res_C;   /* residual added to output channels [0,res_C); res_buf=-1:none
+                                     (res_C < Cout = DownsampleB zero-channel concat,
+                                     models/resnet.py:67-76)                                      */
+  int R, S, stride, pad;
+  int flags;
+} nib_conv_desc;
+
+/* h_weight [Cout][Cin][R][S] fp32 (torch layout), already BN-folded; h_bias [Cout] fp32 or NULL;
+ * h_pre_scale/h_pre_shift [Cin] fp32 when NIB_CONV_PRE_BNRELU. */
+int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight,
+                     const float* h_bias, const float* h_pre_scale, const float* h_pre_shift);
+
+enum nib_pool_kind { NIB_POOL_MAX = 0, NIB_POOL_AVG = 1 };
+/* window k x k, given stride/pad; avg divides by k*k (count_include_pad, as nn.AvgPool2d).
+ * out channels [out_coff, out_coff+C) of out_buf.  Optional per-channel affine+ReLU applied to
+ * the input first (DenseNet transition/norm5: BN-ReLU before the pool commutes only for AVG
+ * when done first, so it is applied to each element before pooling). */
+int nib_net_add_pool(nib_net* net, int kind, int in_buf, int in_coff, int C, int out_buf,
+                     int out_coff, int k, int stride, int pad,
+                     const float* h_pre_scale, const float* h_pre_shift);
+
+/* logits[n][k] = sum_c W[k][c] * feat[n][c] + b[k]; feat = buffer with H=W=1. fp32 math always. */
+int nib_net_add_fc(nib_net* net, int in_buf, int Cin, int Cout, const float* h_weight,
+                   const float* h_bias);
+
+int nib_net_set_input(nib_net* net, int buf);
+int nib_net_finalize(nib_net* net);
+
+/* Input layouts accepted by nib_net_forward */
+enum nib_input_layout {
+  NIB_IN_NCHW_F32 = 0,   /* the reference's tensor: N x C x H x W fp32 (imagenet :245-246)        */
+  NIB_IN_NATIVE = 1      /* already in the input buffer's own layout/dtype (written by
+                            nib_mask_synth with NHWC + the buffer's c_stride/pad)                 */
+};
+
+/* logits: d_logits [N, num_classes] fp32.  N <= max_batch. */
+int nib_net_forward(nib_net* net, const void* d_x, int x_layout, int N, float* d_logits,
+                    void* stream);
+
+/* Fused stages 1+2: masks are synthesised straight into the network's input buffer
+ * (args->d_out/out_dtype/layout/c_stride/pad_* are ignored and taken from the network). */
+int nib_net_forward_masked(nib_net* net, const nib_mask_args* args, float* d_logits, void* stream);
+
+/* Device address + geometry of an activation buffer (MNIST returns x0,x1,x2 besides the logits,
+ * mnist :97-105).  *dtype is nib_dtype.  Layout NHWC, c_stride = C of the buffer. */
+int nib_net_buffer_info(nib_net* net, int buf, void** d_ptr, int* H, int* W, int* C, int* pad,
+                        int* dtype);
+/* NHWC (buffer dtype) -> NCHW fp32 copy of channels [0,C) for N images. */
+int nib_net_read_buffer_nchw(nib_net* net, int buf, int N, float* d_out, void* stream);
+
+/* Counters for bench.py: kernels launched by this handle since creation, and how many of those
+ * were tcgen05 implicit-GEMM launches. */
+int nib_net_launch_counts(nib_net* net, long long* total, long long* tcgen05);
+/* force (1) / forbid (0) the tcgen05 path for eligible convs of a bf16 net (default 1). */
+int nib_net_set_tensor_core(nib_net* net, int enable);
+/* 1 = replay forward through a CUDA graph per batch size (default 0) */
+int nib_net_set_graph(nib_net* net, int enable);
+
+/* Scoring: top-1 index (first maximum, as torch .max(1)), softmax probability of `target`,
+ * max softmax probability, and correct = (top1 == target).
+ * imagenet :248,:257 ; bayesian_active_learning_imagenet.py:196-198 ; mnist :249-259.
+ * Any output pointer may be NULL. */
+int nib_score(const float* d_logits, int N, int K, int target, int32_t* d_top1,
+              float* d_target_prob, float* d_max_prob, uint8_t* d_correct, void* stream);
+
+/* Standalone tcgen05 GEMM self-test hook: C[M,N] = A[M,K] * B[N,K]^T (bf16 in, fp32 out).
+ * Used by tests to validate descriptors independent of the network executor. */
+int nib_tc_gemm_bf16(const void* d_A, const void* d_B, float* d_C, int M, int N, int K,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 3 — Gaussian-process surrogate over binary masks + Expected Improvement
+ * sklearn GaussianProcessRegressor(kernel=RBF(), alpha=1e-5, normalize_y=True) as configured at
+ * BayesianOptimization.py:154-159, arithmetic of sklearn/gaussian_process/_gpr.py (1.9.0).
+ * All matrices fp64, column-major is never used: K and L are row-major [n][ld].
+ * ---------------------------------------------------------------------------------------- */
+
+/* K[i][j] = exp(-0.5 * hamming(z_i, z_j) / l^2) (+ jitter on the diagonal when Zb==Za).
+ * For binary X the sklearn RBF (kernels.py:1561-1569) reduces to this LUT over popcounts.
+ * Za [na,words], Zb [nb,words]; d_K [na][ldk].  d_H (optional, int32 [na][ldk]) receives the
+ * Hamming distances (needed for the LML gradient). */
+int nib_gp_gram_binary(const uint64_t* d_Za, int na, const uint64_t* d_Zb, int nb, int words,
+                       double length_scale, double jitter, double* d_K, int ldk, void* stream);
+
+/* Real-valued RBF Gram: K[i][j] = exp(-0.5*||xa_i - xb_j||^2 / l^2) (+jitter if same & i==j).
+ * Xa [na,d], Xb [nb,d] fp64 row-major.  The reference's actual 1-D firstIndex GP
+ * (BayesianOptimization.py:137-166) uses this with d=1. */
+int nib_gp_gram_rbf(const double* d_Xa, int na, const double* d_Xb, int nb, int d,
+                    double length_scale, double jitter, int same, double* d_K, int ldk,
+                    void* stream);
+
+/* In-place lower Cholesky K = L L^T of the leading n x n block (upper triangle left untouched).
+ * d_info (device int) receives 0 or the 1-based index of the first non-positive pivot
+ * (_gpr.py:352). */
+int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream);
+
+/* Triangular solves with the lower factor L ([n][ldl]) on B ([n][ldb], nrhs columns), in place.
+ * trans=0: B <- L^{-1} B ;  trans=1: B <- L^{-T} B.   (cho_solve = trans 0 then trans 1) */
+int nib_gp_trsm(const double* d_L, int n, int ldl, double* d_B, int nrhs, int ldb, int trans,
+                void* stream);
+
+/* Posterior for m queries given Ks = k(Xq, Xtrain) [m][ldks] (row q = query q):
+ *   mu[q]  = y_std * (Ks[q] . alpha) + y_mean
+ *   var[q] = y_std^2 * max(0, prior_var - || L^{-1} Ks[q]^T ||^2)          (_gpr.py:446-496)
+ * d_work: m*n doubles scratch ([n][m] row-major V).  d_std optional (sqrt(var)). */
+int nib_gp_posterior(const double* d_L, int n, int ldl, const double* d_alpha,
+                     const double* d_Ks, int m, int ldks, double y_mean, double y_std,
+                     double prior_var, double* d_work, double* d_mu, double* d_var,
+                     double* d_std, void* stream);
+
+/* log marginal likelihood and d/d(log l) at the current factor (_gpr.py:588-655):
+ *   lml = -0.5 y^T alpha - sum log L_ii - n/2 log 2pi
+ *   grad = 0.5 * tr((alpha alpha^T - K^{-1}) dK/dtheta),  dK/dtheta = K_noisefree .* D2 / l^2
+ * d_K0: noise-free Gram [n][ld]; d_D2: squared distances [n][ld] (fp64); d_Kinv: K^{-1} [n][ld]
+ * Results to host doubles (synchronises the stream). */
+int nib_gp_lml(const double* d_L, int n, int ldl, const double* d_y, const double* d_alpha,
+               double* h_lml, void* stream);
+int nib_gp_lml_grad(const double* d_K0, const double* d_Kinv, const double* d_alpha,
+                    const uint64_t* d_Z, int words, int n, int ld, double length_scale,
+                    double* h_grad, void* stream);
+
+/* Expected improvement, BayesianOptimization.py:37-54 (returns +EI; the reference returns -EI):
+ *   s = greater_is_better ? 1 : -1;  Z = s*(mu-best)/sigma;  EI = s*(mu-best)*Phi(Z)+sigma*phi(Z)
+ * sigma == 0 yields NaN exactly as the reference (its `== 0.0` line :52 is a no-op comparison).
+ * d_argmax (optional, device int64) = index of the largest non-NaN EI (first on ties). */
+int nib_gp_ei(const double* d_mu, const double* d_sigma, int m, double best,
+              int greater_is_better, double* d_ei, long long* d_argmax, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row 1 — heat map H = sum_i y_i * mask_i  (gp_regression.py:82-94,
+ * gp_superpixel_data_imagenet.py:322-323): per-segment weighted counts scattered to pixels.
+ * d_heat [H*W] fp32;  weights d_y [N] fp32;  keep-mode selection bits.
+ * ---------------------------------------------------------------------------------------- */
+int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S,
+                const uint64_t* d_sel, int sel_words, const float* d_y, int N, float* d_heat,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIB_H_ */

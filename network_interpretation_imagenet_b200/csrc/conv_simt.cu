@@ -1,0 +1,313 @@
+// conv_simt.cu — generic implicit-GEMM convolution on CUDA cores (fp32 accumulate), plus the
+// small layer kernels (pooling, fully-connected, layout transforms).
+//
+// Role: (1) the fp32 parity mode (logits <= 1e-4 vs the reference's fp32 PyTorch forward,
+// generate_gp_training_data_imagenet.py:246), (2) layers the tcgen05 path does not cover
+// (Cin not a multiple of 64: the 3-channel stems, CIFAR ResNet-56 16/32-channel stages,
+// MNIST 1-channel input).  All activations NHWC; weights KRSC ([Cout][R][S][Cin]).
+//
+//   out[m, co] = act( sum_{r,s,c} pre(in[n, p*st-pad+r, q*st-pad+s, c]) * w[co, r, s, c] + bias[co]
+//                     + residual[m, co] )
+#include "common.cuh"
+#include "layers.cuh"
+
+namespace nib {
+
+static constexpr int BM = 128, BN = 64, BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(ConvParams p) {
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  const T* __restrict__ wgt = reinterpret_cast<const T*>(p.w);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+  const T* __restrict__ res = reinterpret_cast<const T*>(p.res);
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int K = p.R * p.S * p.Cin;
+
+  // A-load role: one pixel per thread (tid % 128), 8 consecutive k (tid / 128)
+  const int a_pix = tid & (BM - 1);
+  const int a_k0 = (tid >> 7) * 8;
+  const int am = m0 + a_pix;
+  const bool a_valid = am < p.M;
+  int an = 0, ap = 0, aq = 0;
+  if (a_valid) {
+    an = am / (p.P * p.Q);
+    int rem = am - an * p.P * p.Q;
+    ap = rem / p.Q;
+    aq = rem - ap * p.Q;
+  }
+  const int ih0 = ap * p.stride - p.pad, iw0 = aq * p.stride - p.pad;
+  const int Hp = p.Hin + 2 * p.in_halo, Wp = p.Win + 2 * p.in_halo;
+  const T* in_img = in + (size_t)an * Hp * Wp * p.in_cstride + p.in_coff;
+  const bool cin8 = (p.Cin % 8 == 0) && (p.in_cstride % 8 == 0) && (p.in_coff % 8 == 0);
+
+  // B-load role: cout = tid / 4, 4 consecutive k
+  const int b_co = n0 + (tid >> 2);
+  const int b_k0 = (tid & 3) * 4;
+  const bool kvec = (K % 4 == 0);
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int kb = 0; kb < K; kb += BK) {
+    // ---- gather A ----
+    float av[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) av[j] = 0.f;
+    if (a_valid) {
+      const int k = kb + a_k0;
+      if (cin8) {
+        if (k < K) {
+          const int tap = k / p.Cin, c = k - tap * p.Cin;
+          const int r = tap / p.S, s = tap - r * p.S;
+          const int ih = ih0 + r, iw = iw0 + s;
+          if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win) {
+            const T* src = in_img + ((size_t)(ih + p.in_halo) * Wp + (iw + p.in_halo)) * p.in_cstride + c;
+            if (sizeof(T) == 2) {
+              uint4 raw = *reinterpret_cast<const uint4*>(src);
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) av[j] = __bfloat162float(h[j]);
+            } else {
+              float4 f0 = *reinterpret_cast<const float4*>(src);
+              float4 f1 = *reinterpret_cast<const float4*>(src + 4);
+              av[0] = f0.x; av[1] = f0.y; av[2] = f0.z; av[3] = f0.w;
+              av[4] = f1.x; av[5] = f1.y; av[6] = f1.z; av[7] = f1.w;
+            }
+            if (p.pre_scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                av[j] = fmaxf(fmaf(av[j], p.pre_scale[c + j], p.pre_shift[c + j]), 0.f);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kk = k + j;
+          if (kk < K) {
+            const int tap = kk / p.Cin, c = kk - tap * p.Cin;
+            const int r = tap / p.S, s = tap - r * p.S;
+            const int ih = ih0 + r, iw = iw0 + s;
+            if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win) {
+              float v = Elem<T>::ld(in_img + ((size_t)(ih + p.in_halo) * Wp + (iw + p.in_halo)) * p.in_cstride + c);
+              if (p.pre_scale != nullptr) v = fmaxf(fmaf(v, p.pre_scale[c], p.pre_shift[c]), 0.f);
+              av[j] = v;
+            }
+          }
+        }
+      }
+    }
+    // ---- load B ----
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b_co < p.Cout) {
+      const int k = kb + b_k0;
+      const T* src = wgt + (size_t)b_co * K + k;
+      if (kvec && k + 3 < K) {
+        if (sizeof(T) == 2) {
+          uint2 raw = *reinterpret_cast<const uint2*>(src);
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bv[j] = __bfloat162float(h[j]);
+        } else {
+          float4 f = *reinterpret_cast<const float4*>(src);
+          bv[0] = f.x; bv[1] = f.y; bv[2] = f.z; bv[3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k + j < K) bv[j] = Elem<T>::ld(src + j);
+      }
+    }
+    __syncthreads();  // previous tile fully consumed
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[a_k0 + j][a_pix] = av[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bs[b_k0 + j][tid >> 2] = bv[j];
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+  }
+
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    size_t out_row, res_row = 0;
+    if (p.out_halo == 0) {
+      out_row = (size_t)m * p.out_cstride + p.out_coff;
+    } else {
+      int n = m / (p.P * p.Q), rem = m - n * p.P * p.Q;
+      int pp = rem / p.Q, qq = rem - pp * p.Q;
+      out_row = (((size_t)n * (p.P + 2 * p.out_halo) + pp + p.out_halo) * (p.Q + 2 * p.out_halo) + qq + p.out_halo) *
+                    p.out_cstride + p.out_coff;
+    }
+    if (res != nullptr) res_row = (size_t)m * p.res_cstride + p.res_coff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= p.Cout) continue;
+      float v = acc[i][j];
+      if (p.bias != nullptr) v += p.bias[co];
+      if (res != nullptr && co < p.res_C) v += Elem<T>::ld(res + res_row + co);
+      if (p.relu) v = fmaxf(v, 0.f);
+      Elem<T>::st(out + out_row + co, v);
+    }
+  }
+}
+
+int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st) {
+  dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, BN));
+  if (bf16)
+    conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else
+    conv_simt_kernel<float><<<grid, 256, 0, st>>>(p);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+// ---- pooling ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void pool_kernel(PoolParams p) {
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)p.N * p.P * p.Q * p.C;
+  if (idx >= total) return;
+  int c = (int)(idx % p.C);
+  long long t = idx / p.C;
+  int q = (int)(t % p.Q); t /= p.Q;
+  int pp = (int)(t % p.P);
+  int n = (int)(t / p.P);
+  float acc = p.kind == NIB_POOL_MAX ? -INFINITY : 0.f;
+  for (int r = 0; r < p.k; ++r) {
+    int ih = pp * p.stride - p.pad + r;
+    if (ih < 0 || ih >= p.Hin) continue;
+    for (int s = 0; s < p.k; ++s) {
+      int iw = q * p.stride - p.pad + s;
+      if (iw < 0 || iw >= p.Win) continue;
+      float v = Elem<T>::ld(in + (((size_t)n * p.Hin + ih) * p.Win + iw) * p.in_cstride + p.in_coff + c);
+      if (p.pre_scale != nullptr) v = fmaxf(fmaf(v, p.pre_scale[c], p.pre_shift[c]), 0.f);
+      acc = p.kind == NIB_POOL_MAX ? fmaxf(acc, v) : acc + v;
+    }
+  }
+  if (p.kind == NIB_POOL_AVG) acc = acc / (float)(p.k * p.k);
+  Elem<T>::st(out + (((size_t)n * p.P + pp) * p.Q + q) * p.out_cstride + p.out_coff + c, acc);
+}
+
+int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st) {
+  long long total = (long long)p.N * p.P * p.Q * p.C;
+  unsigned blocks = (unsigned)ceil_div_ll(total, 256);
+  if (bf16)
+    pool_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+  else
+    pool_kernel<float><<<blocks, 256, 0, st>>>(p);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+// ---- fully connected (fp32 weights, fp32 math; features in the net dtype) ---------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+fc_kernel(const T* __restrict__ feat, int feat_stride, const float* __restrict__ w, const float* __restrict__ b,
+          int N, int Cin, int Cout, float* __restrict__ logits) {
+  // one warp per (n, k) output
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)N * Cout) return;
+  const int n = (int)(warp / Cout), k = (int)(warp % Cout);
+  const T* f = feat + (size_t)n * feat_stride;
+  const float* wr = w + (size_t)k * Cin;
+  float acc = 0.f;
+  for (int c = lane; c < Cin; c += 32) acc = fmaf(Elem<T>::ld(f + c), wr[c], acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) logits[(size_t)n * Cout + k] = acc + (b ? b[k] : 0.f);
+}
+
+int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
+              int Cout, float* logits, cudaStream_t st) {
+  unsigned blocks = (unsigned)ceil_div_ll((long long)N * Cout * 32, 256);
+  if (bf16)
+    fc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)feat, feat_stride, w, b, N, Cin, Cout, logits);
+  else
+    fc_kernel<float><<<blocks, 256, 0, st>>>((const float*)feat, feat_stride, w, b, N, Cin, Cout, logits);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+// ---- layout transforms -----------------------------------------------------------------------
+// NCHW fp32 -> NHWC T with channel padding (zeros) and halo offset (halo assumed already zero)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W, T* __restrict__ out,
+                                    int cs, int halo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W;
+  if (idx >= total) return;
+  int w = (int)(idx % W);
+  long long t = idx / W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  T* o = out + (((size_t)n * (H + 2 * halo) + h + halo) * (W + 2 * halo) + w + halo) * cs;
+  for (int c = 0; c < cs; ++c) {
+    float v = c < C ? x[(((size_t)n * C + c) * H + h) * W + w] : 0.f;
+    Elem<T>::st(o + c, v);
+  }
+}
+int launch_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* out, int cs, int halo, bool bf16,
+                        cudaStream_t st) {
+  unsigned blocks = (unsigned)ceil_div_ll((long long)N * H * W, 256);
+  if (bf16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, N, C, H, W, (__nv_bfloat16*)out, cs, halo);
+  else
+    nchw_to_nhwc_kernel<float><<<blocks, 256, 0, st>>>(x, N, C, H, W, (float*)out, cs, halo);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int N, int C, int H, int W, int cs, int halo,
+                                    float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * C * H * W;
+  if (idx >= total) return;
+  int w = (int)(idx % W);
+  long long t = idx / W;
+  int h = (int)(t % H); t /= H;
+  int c = (int)(t % C);
+  int n = (int)(t / C);
+  out[idx] = Elem<T>::ld(in + (((size_t)n * (H + 2 * halo) + h + halo) * (W + 2 * halo) + w + halo) * cs + c);
+}
+int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int halo, bool bf16, float* out,
+                        cudaStream_t st) {
+  unsigned blocks = (unsigned)ceil_div_ll((long long)N * C * H * W, 256);
+  if (bf16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, N, C, H, W, cs, halo, out);
+  else
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, N, C, H, W, cs, halo, out);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+}  // namespace nib

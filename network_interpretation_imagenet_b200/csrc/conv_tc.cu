@@ -1,0 +1,557 @@
+// conv_tc.cu — stage 2 hot kernel: implicit-GEMM convolution on the 5th-gen tensor cores.
+//
+//   out[m, co] = act( sum_k A[m, k] * Wt[co, k] + bias[co] + residual[m, co] ),  bf16 x bf16 -> fp32
+//
+// with m = (n, p, q) flattened output pixels, k = (r, s, c).  A is never materialised:
+//   * 1x1 stride-1 convs read the NHWC activation matrix [N*H*W, C] with a tiled TMA map;
+//   * every other geometry (3x3, strided) uses a TMA *im2col* map: the copy engine walks 128
+//     consecutive output pixels (w fastest, then h, then n) of the padded bounding box and
+//     fetches 64 channels of filter tap (r, s) for each, zero-filling the padding.
+// Both land as a 128 x 64 bf16, 128B-swizzled, K-major tile = one tcgen05.mma operand.
+// Weights are KRSC ([Cout][R*S*Cin], BN folded) and arrive through a second tiled map.
+//
+// CTA = 192 threads, warp-specialised:  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
+// (warp 1 also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> bias /
+// residual / ReLU -> bf16 -> global).  The accumulator (128 lanes x BLOCK_N fp32 columns) lives
+// in TMEM; smem holds a STAGES-deep ring of (A, B) tiles guarded by full/empty mbarriers.
+// Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
+// epilogue overlaps the other's main loop.
+//
+// This replaces the cuDNN calls behind `model(masked_img_tensor)`
+// (generate_gp_training_data_imagenet.py:246, bayesian_active_learning_imagenet.py:192).
+#include "common.cuh"
+#include "layers.cuh"
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+
+namespace nib {
+
+static constexpr int TC_BLOCK_M = 128;
+static constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+static constexpr int TC_UMMA_K = 16;
+static constexpr int TC_THREADS = 192;
+
+struct TcKernelParams {
+  const float* bias;
+  const __nv_bfloat16* res;
+  void* out;
+  int M;            // valid output rows
+  int Cout;
+  int out_cstride, out_coff;
+  int res_cstride, res_coff;
+  int relu;
+  int out_f32;      // 1: store fp32 (GEMM self-test), 0: bf16
+  int num_k_blocks;
+  int cblocks;      // Cin / 64
+  int S;            // filter width (tap -> (r, s))
+  int im2col;       // 0: tiled 2D A map, 1: im2col 4D A map
+  int P, Q, stride, pad;
+  int in_coff;
+  int n_tiles;      // ceil(Cout / BLOCK_N)
+  unsigned int* err_flag;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Bounded wait: a descriptor bug must fail the launch, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+      if (err_flag) atomicExch(err_flag, (unsigned)code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled smem tile (rows of 128 B, 8-row groups 1024 B apart).
+// cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+template <int BLOCK_N>
+__host__ __device__ constexpr uint32_t make_idesc_bf16() {
+  // cute::UMMA::InstrDescriptor: c_format F32=1 @4, a_format BF16=1 @7, b_format BF16=1 @10,
+  // a_major/b_major K=0 @15/@16, N>>3 @17, M>>4 @24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcKernelParams p) {
+  using SM = TcSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + SM::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int m0 = m_tile * TC_BLOCK_M;
+  const int n0 = n_tile * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)(BLOCK_N < 32 ? 32 : BLOCK_N))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int w0 = 0, h0 = 0, img = 0;
+      if (p.im2col) {
+        const int pq = p.P * p.Q;
+        img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int pp = rem / p.Q, qq = rem - pp * p.Q;
+        w0 = qq * p.stride - p.pad;
+        h0 = pp * p.stride - p.pad;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+        const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + SM::A_BYTES;
+        mbar_arrive_expect_tx(full_bar(stage), SM::STAGE_BYTES);
+        const int tap = kb / p.cblocks;
+        const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
+        if (p.im2col) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+        } else {
+          tma_load_2d(a_dst, &tmA, full_bar(stage), c0, m0);
+        }
+        tma_load_2d(b_dst, &tmB, full_bar(stage), kb * TC_BLOCK_K, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
+        const uint32_t b_addr = a_addr + SM::A_BYTES;
+        const uint64_t adesc = make_smem_desc_sw128(a_addr);
+        const uint64_t bdesc = make_smem_desc_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full_bar, 0, p.err_flag, 3);
+    tc_fence_after();
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int cc = 0; cc < BLOCK_N; cc += 32) {
+      uint32_t v[32];
+      __syncwarp();  // .sync.aligned TMEM loads need the full warp converged
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc, v);
+      tmem_ld_wait();
+      const int col0 = n0 + cc;
+      if (row_ok && col0 < p.Cout) {
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+          f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+        }
+      }
+      if (p.res != nullptr) {
+        const __nv_bfloat16* rp = p.res + (size_t)row * p.res_cstride + p.res_coff + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(rp + j);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 r2 = __bfloat1622float2(h2[t]);
+            f[j + 2 * t] += r2.x;
+            f[j + 2 * t + 1] += r2.y;
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (p.out_f32) {
+        float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_cstride + p.out_coff + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.out_cstride + p.out_coff + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          __nv_bfloat162 h;
+          h = __floats2bfloat162_rn(f[j], f[j + 1]);     o.x = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(f[j + 2], f[j + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(f[j + 4], f[j + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(f[j + 6], f[j + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+          *reinterpret_cast<uint4*>(op + j) = o;
+        }
+      }
+      }  // row_ok
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BLOCK_N < 32 ? 32 : BLOCK_N))
+                 : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+
+static int load_driver_fns() {
+  if (g_encodeTiled && g_encodeIm2col) return NIB_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  NIB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled not available"); return NIB_ECUDA; }
+  g_encodeTiled = (PFN_encodeTiled)fn;
+  fn = nullptr;
+  NIB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeIm2col not available"); return NIB_ECUDA; }
+  g_encodeIm2col = (PFN_encodeIm2col)fn;
+  return NIB_OK;
+}
+
+struct TcConvPlan {
+  CUtensorMap tmA, tmB;
+  int block_n, stages;
+  int im2col;
+  int num_k_blocks, cblocks;
+  unsigned int* err_flag;
+};
+
+static unsigned int* g_err_flag = nullptr;
+
+static int encode_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_bytes,
+                          uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu) row_bytes=%llu box=(%u,%u) ptr=%p", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_bytes, box_inner,
+              box_outer, ptr);
+    return NIB_ECUDA;
+  }
+  return NIB_OK;
+}
+
+bool tc_conv_supported(const ConvParams& p) {
+  if (p.Cin % TC_BLOCK_K != 0) return false;
+  if (p.in_cstride % 8 != 0 || p.in_coff % 8 != 0) return false;   // 16 B TMA alignment
+  if (p.Cout % 32 != 0) return false;
+  if (p.out_cstride % 8 != 0 || p.out_coff % 8 != 0) return false;
+  if (p.in_halo != 0 || p.out_halo != 0) return false;
+  if (p.pre_scale != nullptr) return false;                        // pre-activation needs a register path
+  if (p.res != nullptr && (p.res_C != p.Cout || p.res_cstride % 8 != 0 || p.res_coff % 8 != 0)) return false;
+  if (p.R != p.S) return false;
+  if (p.pad > 127 || p.R > 16) return false;
+  return true;
+}
+
+static int pick_block_n(int Cout) {
+  const char* e = getenv("NIB_TC_BLOCK_N");
+  if (e) {
+    int v = atoi(e);
+    if ((v == 32 || v == 64 || v == 128 || v == 256) && Cout % v == 0) return v;
+  }
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  return 32;
+}
+
+int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
+  int rc = load_driver_fns();
+  if (rc != NIB_OK) return rc;
+  if (!g_err_flag) {
+    NIB_CUDA(cudaMalloc(&g_err_flag, sizeof(unsigned int)));
+    NIB_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
+  }
+  TcConvPlan* plan = new TcConvPlan();
+  memset(plan, 0, sizeof(*plan));
+  plan->err_flag = g_err_flag;
+  plan->block_n = pick_block_n(p.Cout);
+  plan->cblocks = p.Cin / TC_BLOCK_K;
+  plan->num_k_blocks = p.R * p.S * plan->cblocks;
+  plan->im2col = !(p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0);
+  const int K = p.R * p.S * p.Cin;
+  // B: weights [Cout][K]
+  rc = encode_2d_bf16(&plan->tmB, p.w, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, TC_BLOCK_K, plan->block_n);
+  if (rc != NIB_OK) { delete plan; return rc; }
+  if (!plan->im2col) {
+    const uint64_t rows = (uint64_t)max_batch * p.Hin * p.Win;
+    rc = encode_2d_bf16(&plan->tmA, p.in, (uint64_t)p.in_cstride, rows, (uint64_t)p.in_cstride * 2, TC_BLOCK_K,
+                        TC_BLOCK_M);
+    if (rc != NIB_OK) { delete plan; return rc; }
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)p.in_cstride, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)max_batch};
+    cuuint64_t strides[3] = {(cuuint64_t)p.in_cstride * 2, (cuuint64_t)p.Win * p.in_cstride * 2,
+                             (cuuint64_t)p.Hin * p.Win * p.in_cstride * 2};
+    int lower[2] = {-p.pad, -p.pad};
+    int upper[2] = {p.pad - (p.S - 1), p.pad - (p.R - 1)};
+    cuuint32_t es[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
+    CUresult r = g_encodeIm2col(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims,
+                                strides, lower, upper, TC_BLOCK_K, TC_BLOCK_M, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeIm2col failed (%d): C=%d W=%d H=%d N=%d R=%d stride=%d pad=%d", (int)r,
+                p.in_cstride, p.Win, p.Hin, max_batch, p.R, p.stride, p.pad);
+      delete plan;
+      return NIB_ECUDA;
+    }
+    // Driver quirk mirrored from CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): for tensors smaller
+    // than 128 KiB, drivers <= 13.1 set a descriptor bit that must be cleared.
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    const uint64_t bytes = (uint64_t)max_batch * p.Hin * p.Win * p.in_cstride * 2;
+    if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&plan->tmA)[1] &= ~(1ull << 21);
+  }
+  *out = plan;
+  return NIB_OK;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+
+template <int BLOCK_N, int STAGES>
+static int launch_tc(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
+  using SM = TcSmem<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NIB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SM::TOTAL));
+    attr_set = true;
+  }
+  conv_tc_kernel<BLOCK_N, STAGES><<<tiles, TC_THREADS, SM::TOTAL, st>>>(plan->tmA, plan->tmB, kp);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
+  switch (plan->block_n) {
+    case 32:  return launch_tc<32, 4>(plan, kp, tiles, st);
+    case 64:  return launch_tc<64, 4>(plan, kp, tiles, st);
+    case 128: return launch_tc<128, 3>(plan, kp, tiles, st);
+    case 256: return launch_tc<256, 4>(plan, kp, tiles, st);
+  }
+  set_error("tc_dispatch: bad block_n %d", plan->block_n);
+  return NIB_EINVAL;
+}
+
+int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st) {
+  TcKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.bias = p.bias;
+  kp.res = reinterpret_cast<const __nv_bfloat16*>(p.res);
+  kp.out = p.out;
+  kp.M = p.M;
+  kp.Cout = p.Cout;
+  kp.out_cstride = p.out_cstride;
+  kp.out_coff = p.out_coff;
+  kp.res_cstride = p.res_cstride;
+  kp.res_coff = p.res_coff;
+  kp.relu = p.relu;
+  kp.out_f32 = 0;
+  kp.num_k_blocks = plan->num_k_blocks;
+  kp.cblocks = plan->cblocks;
+  kp.S = p.S;
+  kp.im2col = plan->im2col;
+  kp.P = p.P;
+  kp.Q = p.Q;
+  kp.stride = p.stride;
+  kp.pad = p.pad;
+  kp.in_coff = p.in_coff;
+  kp.n_tiles = ceil_div(p.Cout, plan->block_n);
+  kp.err_flag = plan->err_flag;
+  const int tiles = ceil_div(p.M, TC_BLOCK_M) * kp.n_tiles;
+  return tc_dispatch(plan, kp, tiles, st);
+}
+
+}  // namespace nib
+
+// Standalone GEMM hook: C[M,N] (fp32) = A[M,K] (bf16) * B[N,K]^T (bf16).  Exercises exactly the
+// descriptors, swizzle and pipeline of the convolution kernel (tiled A map).
+extern "C" int nib_tc_gemm_bf16(const void* d_A, const void* d_B, float* d_C, int M, int N, int K, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  using namespace nib;
+  NIB_REQUIRE(d_A && d_B && d_C, "nib_tc_gemm_bf16: null pointer");
+  NIB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 32 == 0, "nib_tc_gemm_bf16: need K%%64==0, N%%32==0");
+  int rc = load_driver_fns();
+  if (rc != NIB_OK) return rc;
+  if (!g_err_flag) {
+    NIB_CUDA(cudaMalloc(&g_err_flag, sizeof(unsigned int)));
+    NIB_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
+  }
+  TcConvPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  plan.err_flag = g_err_flag;
+  plan.block_n = pick_block_n(N);
+  plan.cblocks = K / TC_BLOCK_K;
+  plan.num_k_blocks = plan.cblocks;
+  plan.im2col = 0;
+  rc = encode_2d_bf16(&plan.tmB, d_B, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, TC_BLOCK_K, plan.block_n);
+  if (rc != NIB_OK) return rc;
+  rc = encode_2d_bf16(&plan.tmA, d_A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, TC_BLOCK_K, TC_BLOCK_M);
+  if (rc != NIB_OK) return rc;
+  TcKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.out = d_C;
+  kp.M = M;
+  kp.Cout = N;
+  kp.out_cstride = N;
+  kp.out_f32 = 1;
+  kp.num_k_blocks = plan.num_k_blocks;
+  kp.cblocks = plan.cblocks;
+  kp.S = 1;
+  kp.n_tiles = ceil_div(N, plan.block_n);
+  kp.err_flag = g_err_flag;
+  const int tiles = ceil_div(M, TC_BLOCK_M) * kp.n_tiles;
+  return tc_dispatch(&plan, kp, tiles, (cudaStream_t)stream);
+}

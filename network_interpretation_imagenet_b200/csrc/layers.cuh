@@ -1,0 +1,54 @@
+// layers.cuh — parameter blocks and launchers shared by the network executor (net.cu).
+#pragma once
+#include "common.cuh"
+
+namespace nib {
+
+struct ConvParams {
+  const void* in;       // NHWC activations (T)
+  const void* w;        // KRSC weights (T)
+  const float* bias;    // [Cout] fp32 or null
+  const void* res;      // residual NHWC (T) or null
+  void* out;
+  const float* pre_scale;  // [Cin] or null (DenseNet pre-activation BN+ReLU on the input)
+  const float* pre_shift;
+  int M;                // N * P * Q output pixels
+  int Hin, Win, Cin, in_cstride, in_coff, in_halo;
+  int P, Q, Cout, out_cstride, out_coff, out_halo;
+  int res_cstride, res_coff, res_C;
+  int R, S, stride, pad;
+  int relu;
+};
+
+struct PoolParams {
+  const void* in;
+  void* out;
+  const float* pre_scale;
+  const float* pre_shift;
+  int kind, N, Hin, Win, C, in_cstride, in_coff;
+  int P, Q, out_cstride, out_coff;
+  int k, stride, pad;
+};
+
+int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st);
+int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st);
+int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
+              int Cout, float* logits, cudaStream_t st);
+int launch_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* out, int cs, int halo, bool bf16,
+                        cudaStream_t st);
+int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int halo, bool bf16, float* out,
+                        cudaStream_t st);
+int mask_synth_impl(const nib_mask_args* a, cudaStream_t st);
+
+// ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ---------------------------------------------
+struct TcConvPlan;  // opaque: tensor maps + tile configuration for one conv layer
+
+// true when the layer geometry is covered by the tcgen05 kernel
+bool tc_conv_supported(const ConvParams& p);
+// builds tensor maps for the given buffers (max_batch images); returns NIB_OK or error
+int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out);
+void tc_conv_plan_destroy(TcConvPlan* plan);
+// launch for a batch with M = N*P*Q valid rows (p.M)
+int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st);
+
+}  // namespace nib

@@ -1,0 +1,470 @@
+// mask_synth.cu — stage 1: superpixel mask synthesis, blend and normalise in one pass.
+//
+// Reference arithmetic (bit-exact targets):
+//   KEEP_MUL       generate_gp_training_data_imagenet.py:234-240
+//                  bayesian_active_learning_imagenet.py:182-187
+//   REMOVE_MINMAX  generate_gp_training_data_mnist.py:218-242, generate_gp_training_data_cifar.py:310-321,
+//                  utils.py:92-94
+//
+// HBM-bound: the only per-mask traffic is the output (C*H*W*sizeof(out) bytes per mask).  One CTA
+// keeps a strip of pixels (labels + C channel values) in registers and loops over a slice of the
+// masks, so the image and label map are read from L2 once per CTA, never once per mask.
+// Stores are 128-bit and streaming (st.global.cs): the masked batch is consumed by the next
+// kernel from HBM/L2, not re-read here.
+#include "common.cuh"
+#include <math.h>
+
+namespace nib {
+
+static constexpr int kMaxC = 4;
+
+__device__ __forceinline__ void st_cs_v4(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_cs_v2(void* p, uint2 v) {
+  asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cs_u32(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Per-mask (min, max-after-subtract) of org*mask for REMOVE_MINMAX, from the per-segment table.
+// fl(v*255) is monotone in v, so the extreme of a kept segment is fl(seg_extreme*255); removed
+// pixels contribute v*0 = 0 (v >= 0 after the a1 rescale).  max(m - mn) = fl(max(m) - mn) by
+// monotonicity of fl(x - c).
+__global__ void mask_stats_kernel(const float* __restrict__ seg_minmax, const uint64_t* __restrict__ sel,
+                                  int words, int N, int S, float2* __restrict__ stats) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float mn = INFINITY, mx = -INFINITY;
+  bool any_removed = false, any = false;
+  for (int s = 0; s < S; ++s) {
+    float smin = seg_minmax[2 * s], smax = seg_minmax[2 * s + 1];
+    if (!(smin <= smax)) continue;  // empty segment (label absent from the map)
+    any = true;
+    bool removed = (sel[(size_t)n * words + (s >> 6)] >> (s & 63)) & 1ull;
+    if (removed) {
+      any_removed = true;
+    } else {
+      mn = fminf(mn, __fmul_rn(smin, 255.0f));
+      mx = fmaxf(mx, __fmul_rn(smax, 255.0f));
+    }
+  }
+  if (any_removed) {
+    mn = fminf(mn, 0.0f);
+    mx = fmaxf(mx, 0.0f);
+  }
+  if (!any) { mn = 0.f; mx = 0.f; }
+  stats[n] = make_float2(mn, __fsub_rn(mx, mn));
+}
+
+template <int MODE>
+__device__ __forceinline__ float blend(float x, bool bit, float mn, float mxs) {
+  if (MODE == NIB_MASK_KEEP_MUL) {
+    // fp32 * uint8 -> fp32 in numpy: the product with an exact 0.0f/1.0f keeps the sign of x on zeros.
+    return __fmul_rn(x, bit ? 1.0f : 0.0f);
+  } else {
+    float t = __fmul_rn(x, bit ? 0.0f : 255.0f);
+    t = __fsub_rn(t, mn);
+    t = __fdiv_rn(t, mxs);
+    t = __fmul_rn(t, 255.0f);
+    return __fmul_rn(t, (float)(1.0 / 255.0));  // np.multiply(f32, 1.0/255.0): weak scalar -> f32
+  }
+}
+
+// VEC pixels per thread along W (VEC=4 needs W % 4 == 0).
+template <typename OutT, int LAYOUT, int MODE, int VEC, typename LabT>
+__global__ void __launch_bounds__(256)
+mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels,
+                  const uint64_t* __restrict__ sel, int words, int N, int C, int H, int W,
+                  const float2* __restrict__ stats, OutT* __restrict__ out, int c_stride, int pad_h,
+                  int pad_w, uint8_t* __restrict__ pixel_mask, int masks_per_cta) {
+  const int HW = H * W;
+  const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (p0 >= HW) return;
+  const int h = p0 / W, w = p0 - h * W;
+
+  int lab[VEC];
+  float x[kMaxC][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) lab[v] = (p0 + v < HW) ? (int)labels[p0 + v] : 0;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) x[c][v] = (c < C && p0 + v < HW) ? img[(size_t)c * HW + p0 + v] : 0.f;
+
+  const int n0 = blockIdx.y * masks_per_cta;
+  const int n1 = min(N, n0 + masks_per_cta);
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+
+  for (int n = n0; n < n1; ++n) {
+    bool bit[VEC];
+    if (words == 1) {
+      const uint64_t z = __ldg(sel + n);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) bit[v] = (z >> lab[v]) & 1ull;
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        bit[v] = (__ldg(sel + (size_t)n * words + (lab[v] >> 6)) >> (lab[v] & 63)) & 1ull;
+    }
+    float mn = 0.f, mxs = 1.f;
+    if (MODE == NIB_MASK_REMOVE_MINMAX) {
+      float2 st = __ldg(stats + n);
+      mn = st.x;
+      mxs = st.y;
+    }
+    float y[kMaxC][VEC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) y[c][v] = blend<MODE>(x[c][v], bit[v], mn, mxs);
+
+    if (pixel_mask != nullptr) {
+      uint8_t mv[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        mv[v] = (MODE == NIB_MASK_KEEP_MUL) ? (bit[v] ? 1 : 0) : (bit[v] ? 0 : 255);
+      uint8_t* pm = pixel_mask + (size_t)n * HW + p0;
+      if (VEC == 4) {
+        st_cs_u32(pm, (uint32_t)mv[0] | ((uint32_t)mv[1] << 8) | ((uint32_t)mv[2] << 16) |
+                          ((uint32_t)mv[3 % VEC] << 24));
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if (p0 + v < HW) pm[v] = mv[v];
+      }
+    }
+
+    if (LAYOUT == NIB_NCHW) {
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) {
+        if (c >= C) break;
+        OutT* o = out + ((size_t)n * C + c) * HW + p0;
+        if (VEC == 4) {
+          if (sizeof(OutT) == 4) {
+            st_cs_v4(o, make_uint4(__float_as_uint(y[c][0]), __float_as_uint(y[c][1 % VEC]),
+                                   __float_as_uint(y[c][2 % VEC]), __float_as_uint(y[c][3 % VEC])));
+          } else {
+            st_cs_v2(o, make_uint2(pack_bf16x2(y[c][0], y[c][1 % VEC]),
+                                   pack_bf16x2(y[c][2 % VEC], y[c][3 % VEC])));
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            if (p0 + v < HW) Elem<OutT>::st(o + v, y[c][v]);
+        }
+      }
+    } else {  // NHWC with channel padding and halo offset
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (p0 + v >= HW) break;
+        OutT* o = out + (((size_t)n * Hp + (h + pad_h)) * Wp + (w + v + pad_w)) * c_stride;
+        if (sizeof(OutT) == 2 && c_stride == 8) {
+          st_cs_v4(o, make_uint4(pack_bf16x2(y[0][v], y[1][v]), pack_bf16x2(y[2][v], y[3][v]), 0u, 0u));
+        } else if (sizeof(OutT) == 2 && c_stride == 4) {
+          st_cs_v2(o, make_uint2(pack_bf16x2(y[0][v], y[1][v]), pack_bf16x2(y[2][v], y[3][v])));
+        } else if (sizeof(OutT) == 4 && c_stride == 4) {
+          st_cs_v4(o, make_uint4(__float_as_uint(y[0][v]), __float_as_uint(y[1][v]),
+                                 __float_as_uint(y[2][v]), __float_as_uint(y[3][v])));
+        } else {
+          for (int c = 0; c < c_stride; ++c) {
+            float val = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < kMaxC; ++cc)
+              if (cc == c) val = y[cc][v];
+            Elem<OutT>::st(o + c, (c < C) ? val : 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+// zero the halo ring of an NHWC padded batch
+template <typename OutT>
+__global__ void halo_zero_kernel(OutT* out, int N, int H, int W, int c_stride, int pad_h, int pad_w) {
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  const int halo = Hp * Wp - H * W;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * halo;
+  if (idx >= total) return;
+  int n = (int)(idx / halo), r = (int)(idx - (long long)n * halo);
+  int hp, wp;
+  const int top = pad_h * Wp;
+  if (r < top) {
+    hp = r / Wp; wp = r - hp * Wp;
+  } else if (r < 2 * top) {
+    int q = r - top;
+    hp = H + pad_h + q / Wp; wp = q % Wp;
+  } else {
+    int q = r - 2 * top;            // side columns of the H interior rows
+    int row = q / (2 * pad_w), col = q - row * (2 * pad_w);
+    hp = pad_h + row;
+    wp = col < pad_w ? col : (W + pad_w + (col - pad_w));
+  }
+  OutT* o = out + (((size_t)n * Hp + hp) * Wp + wp) * c_stride;
+  for (int c = 0; c < c_stride; ++c) Elem<OutT>::st(o + c, 0.f);
+}
+
+// ---- per-segment min/max --------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int k) {
+  return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+__global__ void segmm_init_kernel(int* tab, int S) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S) {
+    tab[2 * s] = float_to_ordered(INFINITY);
+    tab[2 * s + 1] = float_to_ordered(-INFINITY);
+  }
+}
+template <typename LabT>
+__global__ void segmm_accum_kernel(const float* __restrict__ img, const LabT* __restrict__ labels, int C,
+                                   int HW, int S, int* tab) {
+  extern __shared__ int sm[];  // [2*S]
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    sm[2 * i] = float_to_ordered(INFINITY);
+    sm[2 * i + 1] = float_to_ordered(-INFINITY);
+  }
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int lab = (int)labels[p];
+    if (lab >= S) continue;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      float v = img[(size_t)c * HW + p];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+    atomicMin(&sm[2 * lab], float_to_ordered(mn));
+    atomicMax(&sm[2 * lab + 1], float_to_ordered(mx));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    atomicMin(&tab[2 * i], sm[2 * i]);
+    atomicMax(&tab[2 * i + 1], sm[2 * i + 1]);
+  }
+}
+__global__ void segmm_decode_kernel(int* tab, int S) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * S) reinterpret_cast<float*>(tab)[i] = ordered_to_float(tab[i]);
+}
+
+// ---- a1: per-image min-max rescale to [0,255] ------------------------------------------------
+__global__ void prep_minmax_kernel(float* org, int C, int H, int W, uint8_t* u8) {
+  __shared__ float s_mn[32], s_mx[32];
+  __shared__ float g_mn, g_mx;
+  const int total = C * H * W;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    float v = org[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = INFINITY, b = -INFINITY;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { a = fminf(a, s_mn[i]); b = fmaxf(b, s_mx[i]); }
+    g_mn = a;
+    g_mx = __fsub_rn(b, a);  // max of (x - min) == fl(max - min)
+  }
+  __syncthreads();
+  const float a = g_mn, b = g_mx;
+  const int HW = H * W;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    float v = __fsub_rn(org[i], a);
+    v = __fdiv_rn(v, b);
+    v = __fmul_rn(v, 255.0f);
+    org[i] = v;
+    if (u8) {
+      int c = i / HW, p = i - c * HW;
+      u8[(size_t)p * C + c] = (uint8_t)v;  // astype(np.uint8) truncates
+    }
+  }
+}
+
+// ---- heat map --------------------------------------------------------------------------------
+__global__ void heat_weights_kernel(const uint64_t* __restrict__ sel, int words, const float* __restrict__ y,
+                                    int N, int S, double* __restrict__ wseg) {
+  // one block per segment; exact for integer-valued labels (gp_regression.py:82-94 adds ints)
+  const int s = blockIdx.x;
+  double acc = 0.0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x)
+    if ((sel[(size_t)n * words + (s >> 6)] >> (s & 63)) & 1ull) acc += (double)y[n];
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    wseg[s] = t;
+  }
+}
+template <typename LabT>
+__global__ void heat_scatter_kernel(const LabT* __restrict__ labels, int HW, int S,
+                                    const double* __restrict__ wseg, float* __restrict__ heat) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < HW) {
+    int lab = (int)labels[p];
+    heat[p] = lab < S ? (float)wseg[lab] : 0.f;
+  }
+}
+
+template <typename OutT, int LAYOUT, int MODE, typename LabT>
+static int launch_mask(const nib_mask_args* a, const float2* stats, cudaStream_t st) {
+  const int HW = a->H * a->W;
+  const bool vec4 = (a->W % 4 == 0);
+  const int threads = 256;
+  const int per = vec4 ? 4 : 1;
+  const int gx = ceil_div(ceil_div(HW, per), threads);
+  // enough CTAs for >= 4 waves of 148 SMs x 8 resident CTAs when N allows
+  int target_ctas = num_sms() * 16;
+  int gy = max(1, min(a->N, ceil_div(target_ctas, gx)));
+  int mpc = ceil_div(a->N, gy);
+  gy = ceil_div(a->N, mpc);
+  dim3 grid(gx, gy);
+  if (vec4)
+    mask_synth_kernel<OutT, LAYOUT, MODE, 4, LabT><<<grid, threads, 0, st>>>(
+        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, stats,
+        (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc);
+  else
+    mask_synth_kernel<OutT, LAYOUT, MODE, 1, LabT><<<grid, threads, 0, st>>>(
+        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, stats,
+        (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc);
+  NIB_LAUNCH_CHECK();
+  if (LAYOUT == NIB_NHWC && (a->pad_h > 0 || a->pad_w > 0)) {
+    const int Hp = a->H + 2 * a->pad_h, Wp = a->W + 2 * a->pad_w;
+    long long total = (long long)a->N * (Hp * Wp - HW);
+    halo_zero_kernel<OutT><<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
+        (OutT*)a->d_out, a->N, a->H, a->W, a->c_stride, a->pad_h, a->pad_w);
+    NIB_LAUNCH_CHECK();
+  }
+  return NIB_OK;
+}
+
+template <typename OutT, int LAYOUT, typename LabT>
+static int dispatch_mode(const nib_mask_args* a, const float2* stats, cudaStream_t st) {
+  if (a->mode == NIB_MASK_KEEP_MUL) return launch_mask<OutT, LAYOUT, NIB_MASK_KEEP_MUL, LabT>(a, stats, st);
+  return launch_mask<OutT, LAYOUT, NIB_MASK_REMOVE_MINMAX, LabT>(a, stats, st);
+}
+template <typename OutT, typename LabT>
+static int dispatch_layout(const nib_mask_args* a, const float2* stats, cudaStream_t st) {
+  if (a->layout == NIB_NCHW) return dispatch_mode<OutT, NIB_NCHW, LabT>(a, stats, st);
+  return dispatch_mode<OutT, NIB_NHWC, LabT>(a, stats, st);
+}
+
+// scratch for per-mask stats, grown on demand (per process; stream-ordered use)
+static float2* g_stats = nullptr;
+static int g_stats_cap = 0;
+
+int mask_synth_impl(const nib_mask_args* a, cudaStream_t st) {
+  NIB_REQUIRE(a != nullptr, "nib_mask_synth: null args");
+  NIB_REQUIRE(a->d_img && a->d_labels && a->d_sel && a->d_out, "nib_mask_synth: null device pointer");
+  NIB_REQUIRE(a->N >= 0 && a->C >= 1 && a->C <= kMaxC, "nib_mask_synth: C=%d unsupported (1..%d)", a->C, kMaxC);
+  NIB_REQUIRE(a->H > 0 && a->W > 0 && a->S > 0, "nib_mask_synth: bad geometry H=%d W=%d S=%d", a->H, a->W, a->S);
+  NIB_REQUIRE(a->label_bytes == 1 || a->label_bytes == 2, "nib_mask_synth: label_bytes must be 1 or 2");
+  NIB_REQUIRE(a->label_bytes == 2 || a->S <= 256, "nib_mask_synth: S=%d needs uint16 labels", a->S);
+  NIB_REQUIRE(a->sel_words * 64 >= a->S, "nib_mask_synth: sel_words=%d too small for S=%d", a->sel_words, a->S);
+  NIB_REQUIRE(a->mode == NIB_MASK_KEEP_MUL || a->mode == NIB_MASK_REMOVE_MINMAX, "nib_mask_synth: bad mode %d", a->mode);
+  NIB_REQUIRE(a->out_dtype == NIB_F32 || a->out_dtype == NIB_BF16, "nib_mask_synth: bad out_dtype");
+  NIB_REQUIRE(a->layout == NIB_NCHW || a->layout == NIB_NHWC, "nib_mask_synth: bad layout");
+  if (a->layout == NIB_NHWC)
+    NIB_REQUIRE(a->c_stride >= a->C && a->pad_h >= 0 && a->pad_w >= 0, "nib_mask_synth: bad NHWC c_stride/pad");
+  if (a->N == 0) return NIB_OK;
+  const float2* stats = nullptr;
+  if (a->mode == NIB_MASK_REMOVE_MINMAX) {
+    NIB_REQUIRE(a->d_seg_minmax != nullptr, "nib_mask_synth: REMOVE_MINMAX needs d_seg_minmax (nib_segment_minmax)");
+    if (g_stats_cap < a->N) {
+      if (g_stats) cudaFree(g_stats);
+      g_stats_cap = max(a->N, 4096);
+      NIB_CUDA(cudaMalloc(&g_stats, sizeof(float2) * g_stats_cap));
+    }
+    mask_stats_kernel<<<ceil_div(a->N, 128), 128, 0, st>>>(a->d_seg_minmax, a->d_sel, a->sel_words, a->N, a->S, g_stats);
+    NIB_LAUNCH_CHECK();
+    stats = g_stats;
+  }
+  if (a->out_dtype == NIB_F32) {
+    if (a->label_bytes == 1) return dispatch_layout<float, uint8_t>(a, stats, st);
+    return dispatch_layout<float, uint16_t>(a, stats, st);
+  } else {
+    if (a->label_bytes == 1) return dispatch_layout<__nv_bfloat16, uint8_t>(a, stats, st);
+    return dispatch_layout<__nv_bfloat16, uint16_t>(a, stats, st);
+  }
+}
+
+}  // namespace nib
+
+extern "C" {
+
+int nib_mask_synth(const nib_mask_args* args, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  return nib::mask_synth_impl(args, (cudaStream_t)stream);
+}
+
+int nib_segment_minmax(const float* d_img, const void* d_labels, int label_bytes, int C, int H, int W,
+                       int S, float* d_seg_minmax, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_img && d_labels && d_seg_minmax, "nib_segment_minmax: null pointer");
+  NIB_REQUIRE(S > 0 && S <= 4096 && C > 0 && H > 0 && W > 0, "nib_segment_minmax: bad geometry");
+  NIB_REQUIRE(label_bytes == 1 || label_bytes == 2, "nib_segment_minmax: label_bytes must be 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* tab = reinterpret_cast<int*>(d_seg_minmax);
+  nib::segmm_init_kernel<<<nib::ceil_div(S, 128), 128, 0, st>>>(tab, S);
+  const int HW = H * W;
+  int blocks = min(nib::ceil_div(HW, 256), 64);
+  size_t smem = sizeof(int) * 2 * S;
+  if (label_bytes == 1)
+    nib::segmm_accum_kernel<uint8_t><<<blocks, 256, smem, st>>>(d_img, (const uint8_t*)d_labels, C, HW, S, tab);
+  else
+    nib::segmm_accum_kernel<uint16_t><<<blocks, 256, smem, st>>>(d_img, (const uint16_t*)d_labels, C, HW, S, tab);
+  nib::segmm_decode_kernel<<<nib::ceil_div(2 * S, 128), 128, 0, st>>>(tab, S);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+int nib_prep_minmax_u8(float* d_org, int C, int H, int W, uint8_t* d_u8, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_org && C > 0 && H > 0 && W > 0, "nib_prep_minmax_u8: bad arguments");
+  nib::prep_minmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_org, C, H, W, d_u8);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S, const uint64_t* d_sel,
+                int sel_words, const float* d_y, int N, float* d_heat, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_labels && d_sel && d_y && d_heat, "nib_heatmap: null pointer");
+  NIB_REQUIRE(S > 0 && S <= 4096 && sel_words * 64 >= S, "nib_heatmap: bad S/sel_words");
+  NIB_REQUIRE(label_bytes == 1 || label_bytes == 2, "nib_heatmap: label_bytes must be 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  static double* wseg = nullptr;
+  if (!wseg) NIB_CUDA(cudaMalloc(&wseg, sizeof(double) * 4096));
+  nib::heat_weights_kernel<<<S, 256, 0, st>>>(d_sel, sel_words, d_y, N, S, wseg);
+  const int HW = H * W;
+  if (label_bytes == 1)
+    nib::heat_scatter_kernel<uint8_t><<<nib::ceil_div(HW, 256), 256, 0, st>>>((const uint8_t*)d_labels, HW, S, wseg, d_heat);
+  else
+    nib::heat_scatter_kernel<uint16_t><<<nib::ceil_div(HW, 256), 256, 0, st>>>((const uint16_t*)d_labels, HW, S, wseg, d_heat);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,446 @@
+// net.cu — classifier executor: a flat op list over NHWC activation buffers (include/nib.h §Stage 2).
+//
+// The host mirror (classifier.py) walks the reference's nn.Module (models/resnet.py:79-146,
+// models/densenet.py:44-99, generate_gp_training_data_mnist.py:86-105, torchvision resnet101 /
+// densenet121 as loaded at generate_gp_training_data_imagenet.py:579), folds eval-mode BatchNorm
+// into conv weights/bias and emits the ops.  This file owns device weights (packed KRSC), the
+// activation buffers sized for max_batch, per-layer tcgen05 plans, and the launch sequence.
+#include "common.cuh"
+#include "layers.cuh"
+#include <vector>
+#include <map>
+#include <string.h>
+
+using namespace nib;
+
+struct NetBuffer {
+  int H, W, C, pad;
+  void* ptr;
+  size_t elems_per_image;
+};
+
+struct NetOp {
+  int kind;  // 0 conv, 1 pool, 2 fc
+  nib_conv_desc cd;
+  void* d_w;          // conv: KRSC in net dtype; fc: fp32 [Cout][Cin]
+  float* d_bias;
+  float* d_pre_scale;
+  float* d_pre_shift;
+  TcConvPlan* plan;
+  // pool
+  int pool_kind, k, stride, pad, C, in_buf, in_coff, out_buf, out_coff;
+  // fc
+  int fc_in, fc_cin, fc_cout;
+};
+
+struct nib_net {
+  int precision;
+  int max_batch;
+  bool bf16;
+  std::vector<NetBuffer> bufs;
+  std::vector<NetOp> ops;
+  int input_buf;
+  bool finalized;
+  int num_classes;
+  bool use_tc;
+  bool use_graph;
+  long long launches, tc_launches;
+  struct GraphKey {
+    int N, layout;
+    const void* x;
+    float* logits;
+    bool operator<(const GraphKey& o) const {
+      if (N != o.N) return N < o.N;
+      if (layout != o.layout) return layout < o.layout;
+      if (x != o.x) return x < o.x;
+      return logits < o.logits;
+    }
+  };
+  struct GraphVal { cudaGraphExec_t exec; long long launches, tc_launches; };
+  std::map<GraphKey, GraphVal> graphs;
+};
+
+static size_t elem_size(const nib_net* n) { return n->bf16 ? 2 : 4; }
+
+static int upload_floats(const float* h, size_t n, float** d) {
+  *d = nullptr;
+  if (!h || n == 0) return NIB_OK;
+  NIB_CUDA(cudaMalloc(d, n * sizeof(float)));
+  NIB_CUDA(cudaMemcpy(*d, h, n * sizeof(float), cudaMemcpyHostToDevice));
+  return NIB_OK;
+}
+
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+extern "C" {
+
+int nib_net_create(int precision, int max_batch, nib_net** out) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(out != nullptr, "nib_net_create: null out");
+  NIB_REQUIRE(precision == NIB_PREC_FP32 || precision == NIB_PREC_BF16, "nib_net_create: bad precision %d", precision);
+  NIB_REQUIRE(max_batch > 0, "nib_net_create: max_batch must be > 0");
+  nib_net* n = new nib_net();
+  n->precision = precision;
+  n->bf16 = precision == NIB_PREC_BF16;
+  n->max_batch = max_batch;
+  n->input_buf = -1;
+  n->finalized = false;
+  n->num_classes = 0;
+  n->use_tc = true;
+  n->use_graph = false;
+  n->launches = n->tc_launches = 0;
+  *out = n;
+  return NIB_OK;
+}
+
+int nib_net_destroy(nib_net* net) {
+  if (!net) return NIB_OK;
+  for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
+  for (auto& b : net->bufs)
+    if (b.ptr) cudaFree(b.ptr);
+  for (auto& o : net->ops) {
+    if (o.d_w) cudaFree(o.d_w);
+    if (o.d_bias) cudaFree(o.d_bias);
+    if (o.d_pre_scale) cudaFree(o.d_pre_scale);
+    if (o.d_pre_shift) cudaFree(o.d_pre_shift);
+    if (o.plan) tc_conv_plan_destroy(o.plan);
+  }
+  delete net;
+  return NIB_OK;
+}
+
+int nib_net_add_buffer(nib_net* net, int H, int W, int C, int pad) {
+  NIB_REQUIRE(net && !net->finalized, "nib_net_add_buffer: bad handle/state");
+  NIB_REQUIRE(H > 0 && W > 0 && C > 0 && pad >= 0, "nib_net_add_buffer: bad geometry");
+  NetBuffer b;
+  b.H = H; b.W = W; b.C = C; b.pad = pad;
+  b.elems_per_image = (size_t)(H + 2 * pad) * (W + 2 * pad) * C;
+  size_t bytes = b.elems_per_image * net->max_batch * elem_size(net);
+  // one extra tile row block of slack: TMA boxes never read past the tensor-map extent, but SIMT
+  // vector loads on the last pixel may touch up to 16 B beyond the last channel group.
+  NIB_CUDA(cudaMalloc(&b.ptr, bytes + 256));
+  NIB_CUDA(cudaMemset(b.ptr, 0, bytes + 256));
+  net->bufs.push_back(b);
+  return (int)net->bufs.size() - 1;
+}
+
+int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight, const float* h_bias,
+                     const float* h_pre_scale, const float* h_pre_shift) {
+  NIB_REQUIRE(net && !net->finalized && d && h_weight, "nib_net_add_conv: bad handle/state/args");
+  const int nb = (int)net->bufs.size();
+  NIB_REQUIRE(d->in_buf >= 0 && d->in_buf < nb && d->out_buf >= 0 && d->out_buf < nb, "nib_net_add_conv: bad buffer id");
+  NIB_REQUIRE(d->res_buf < nb, "nib_net_add_conv: bad residual buffer id");
+  const NetBuffer& bi = net->bufs[d->in_buf];
+  const NetBuffer& bo = net->bufs[d->out_buf];
+  NIB_REQUIRE(d->in_coff >= 0 && d->in_coff + d->Cin <= bi.C, "nib_net_add_conv: input channel slice out of range");
+  NIB_REQUIRE(d->out_coff >= 0 && d->out_coff + d->Cout <= bo.C, "nib_net_add_conv: output channel slice out of range");
+  NIB_REQUIRE(d->R > 0 && d->S > 0 && d->stride > 0 && d->pad >= 0, "nib_net_add_conv: bad filter geometry");
+  const int P = (bi.H + 2 * d->pad - d->R) / d->stride + 1;
+  const int Q = (bi.W + 2 * d->pad - d->S) / d->stride + 1;
+  NIB_REQUIRE(P == bo.H && Q == bo.W, "nib_net_add_conv: output buffer is %dx%d but conv produces %dx%d", bo.H, bo.W, P, Q);
+  NIB_REQUIRE(bo.pad == 0, "nib_net_add_conv: output buffers with halo are not supported");
+  if (d->res_buf >= 0) {
+    const NetBuffer& br = net->bufs[d->res_buf];
+    NIB_REQUIRE(br.H == bo.H && br.W == bo.W && br.pad == 0, "nib_net_add_conv: residual geometry mismatch");
+    NIB_REQUIRE(d->res_C > 0 && d->res_C <= d->Cout && d->res_coff + d->res_C <= br.C, "nib_net_add_conv: residual channels out of range");
+  }
+  if (d->flags & NIB_CONV_PRE_BNRELU) NIB_REQUIRE(h_pre_scale && h_pre_shift, "nib_net_add_conv: PRE_BNRELU needs scale/shift");
+
+  NetOp op;
+  memset(&op, 0, sizeof(op));
+  op.kind = 0;
+  op.cd = *d;
+  const size_t K = (size_t)d->R * d->S * d->Cin;
+  const size_t nel = K * d->Cout;
+  // [Cout][Cin][R][S] -> [Cout][R][S][Cin]
+  std::vector<float> krsc(nel);
+  for (int co = 0; co < d->Cout; ++co)
+    for (int c = 0; c < d->Cin; ++c)
+      for (int r = 0; r < d->R; ++r)
+        for (int s = 0; s < d->S; ++s)
+          krsc[(((size_t)co * d->R + r) * d->S + s) * d->Cin + c] =
+              h_weight[(((size_t)co * d->Cin + c) * d->R + r) * d->S + s];
+  if (net->bf16) {
+    std::vector<uint16_t> hb(nel);
+    for (size_t i = 0; i < nel; ++i) hb[i] = f32_to_bf16_rn(krsc[i]);
+    NIB_CUDA(cudaMalloc(&op.d_w, nel * 2 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w, hb.data(), nel * 2, cudaMemcpyHostToDevice));
+  } else {
+    NIB_CUDA(cudaMalloc(&op.d_w, nel * 4 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w, krsc.data(), nel * 4, cudaMemcpyHostToDevice));
+  }
+  int rc = upload_floats(h_bias, d->Cout, &op.d_bias);
+  if (rc != NIB_OK) return rc;
+  if (d->flags & NIB_CONV_PRE_BNRELU) {
+    rc = upload_floats(h_pre_scale, d->Cin, &op.d_pre_scale);
+    if (rc != NIB_OK) return rc;
+    rc = upload_floats(h_pre_shift, d->Cin, &op.d_pre_shift);
+    if (rc != NIB_OK) return rc;
+  }
+  net->ops.push_back(op);
+  return NIB_OK;
+}
+
+int nib_net_add_pool(nib_net* net, int kind, int in_buf, int in_coff, int C, int out_buf, int out_coff, int k,
+                     int stride, int pad, const float* h_pre_scale, const float* h_pre_shift) {
+  NIB_REQUIRE(net && !net->finalized, "nib_net_add_pool: bad handle/state");
+  const int nb = (int)net->bufs.size();
+  NIB_REQUIRE(in_buf >= 0 && in_buf < nb && out_buf >= 0 && out_buf < nb, "nib_net_add_pool: bad buffer id");
+  NIB_REQUIRE(kind == NIB_POOL_MAX || kind == NIB_POOL_AVG, "nib_net_add_pool: bad kind");
+  const NetBuffer& bi = net->bufs[in_buf];
+  const NetBuffer& bo = net->bufs[out_buf];
+  NIB_REQUIRE(bi.pad == 0 && bo.pad == 0, "nib_net_add_pool: halo buffers unsupported");
+  NIB_REQUIRE(in_coff + C <= bi.C && out_coff + C <= bo.C, "nib_net_add_pool: channel slice out of range");
+  const int P = (bi.H + 2 * pad - k) / stride + 1, Q = (bi.W + 2 * pad - k) / stride + 1;
+  NIB_REQUIRE(P == bo.H && Q == bo.W, "nib_net_add_pool: output buffer is %dx%d but pool produces %dx%d", bo.H, bo.W, P, Q);
+  NetOp op;
+  memset(&op, 0, sizeof(op));
+  op.kind = 1;
+  op.pool_kind = kind; op.k = k; op.stride = stride; op.pad = pad; op.C = C;
+  op.in_buf = in_buf; op.in_coff = in_coff; op.out_buf = out_buf; op.out_coff = out_coff;
+  int rc = upload_floats(h_pre_scale, C, &op.d_pre_scale);
+  if (rc != NIB_OK) return rc;
+  rc = upload_floats(h_pre_shift, C, &op.d_pre_shift);
+  if (rc != NIB_OK) return rc;
+  net->ops.push_back(op);
+  return NIB_OK;
+}
+
+int nib_net_add_fc(nib_net* net, int in_buf, int Cin, int Cout, const float* h_weight, const float* h_bias) {
+  NIB_REQUIRE(net && !net->finalized && h_weight, "nib_net_add_fc: bad handle/state/args");
+  NIB_REQUIRE(in_buf >= 0 && in_buf < (int)net->bufs.size(), "nib_net_add_fc: bad buffer id");
+  const NetBuffer& bi = net->bufs[in_buf];
+  NIB_REQUIRE(bi.H == 1 && bi.W == 1 && bi.C >= Cin, "nib_net_add_fc: input must be a 1x1xC feature buffer");
+  NetOp op;
+  memset(&op, 0, sizeof(op));
+  op.kind = 2;
+  op.fc_in = in_buf; op.fc_cin = Cin; op.fc_cout = Cout;
+  float* w = nullptr;
+  int rc = upload_floats(h_weight, (size_t)Cin * Cout, &w);
+  if (rc != NIB_OK) return rc;
+  op.d_w = w;
+  rc = upload_floats(h_bias, Cout, &op.d_bias);
+  if (rc != NIB_OK) return rc;
+  net->ops.push_back(op);
+  net->num_classes = Cout;
+  return NIB_OK;
+}
+
+int nib_net_set_input(nib_net* net, int buf) {
+  NIB_REQUIRE(net && buf >= 0 && buf < (int)net->bufs.size(), "nib_net_set_input: bad buffer id");
+  net->input_buf = buf;
+  return NIB_OK;
+}
+
+static void fill_conv_params(const nib_net* net, const NetOp& op, int N, ConvParams* p) {
+  const nib_conv_desc& d = op.cd;
+  const NetBuffer& bi = net->bufs[d.in_buf];
+  const NetBuffer& bo = net->bufs[d.out_buf];
+  memset(p, 0, sizeof(*p));
+  p->in = bi.ptr;
+  p->w = op.d_w;
+  p->bias = op.d_bias;
+  p->out = bo.ptr;
+  p->pre_scale = op.d_pre_scale;
+  p->pre_shift = op.d_pre_shift;
+  p->Hin = bi.H; p->Win = bi.W; p->Cin = d.Cin; p->in_cstride = bi.C; p->in_coff = d.in_coff; p->in_halo = bi.pad;
+  p->P = bo.H; p->Q = bo.W; p->Cout = d.Cout; p->out_cstride = bo.C; p->out_coff = d.out_coff; p->out_halo = bo.pad;
+  p->M = N * bo.H * bo.W;
+  if (d.res_buf >= 0) {
+    const NetBuffer& br = net->bufs[d.res_buf];
+    p->res = br.ptr;
+    p->res_cstride = br.C; p->res_coff = d.res_coff; p->res_C = d.res_C;
+  }
+  p->R = d.R; p->S = d.S; p->stride = d.stride; p->pad = d.pad;
+  p->relu = (d.flags & NIB_CONV_RELU) ? 1 : 0;
+}
+
+int nib_net_finalize(nib_net* net) {
+  NIB_REQUIRE(net && !net->finalized, "nib_net_finalize: bad handle/state");
+  NIB_REQUIRE(net->input_buf >= 0, "nib_net_finalize: input buffer not set");
+  NIB_REQUIRE(!net->ops.empty() && net->ops.back().kind == 2, "nib_net_finalize: the last op must be the fc layer");
+  if (net->bf16) {
+    for (auto& op : net->ops) {
+      if (op.kind != 0) continue;
+      ConvParams p;
+      fill_conv_params(net, op, net->max_batch, &p);
+      if (tc_conv_supported(p)) {
+        int rc = tc_conv_plan_create(p, net->max_batch, &op.plan);
+        if (rc != NIB_OK) return rc;
+      }
+    }
+  }
+  net->finalized = true;
+  return NIB_OK;
+}
+
+static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
+  for (auto& op : net->ops) {
+    if (op.kind == 0) {
+      ConvParams p;
+      fill_conv_params(net, op, N, &p);
+      int rc;
+      if (op.plan && net->use_tc) {
+        rc = tc_conv_launch(op.plan, p, st);
+        net->tc_launches++;
+      } else {
+        rc = launch_conv_simt(p, net->bf16, st);
+      }
+      net->launches++;
+      if (rc != NIB_OK) return rc;
+    } else if (op.kind == 1) {
+      const NetBuffer& bi = net->bufs[op.in_buf];
+      const NetBuffer& bo = net->bufs[op.out_buf];
+      PoolParams p;
+      memset(&p, 0, sizeof(p));
+      p.in = bi.ptr; p.out = bo.ptr;
+      p.pre_scale = op.d_pre_scale; p.pre_shift = op.d_pre_shift;
+      p.kind = op.pool_kind; p.N = N; p.Hin = bi.H; p.Win = bi.W; p.C = op.C;
+      p.in_cstride = bi.C; p.in_coff = op.in_coff;
+      p.P = bo.H; p.Q = bo.W; p.out_cstride = bo.C; p.out_coff = op.out_coff;
+      p.k = op.k; p.stride = op.stride; p.pad = op.pad;
+      int rc = launch_pool(p, net->bf16, st);
+      net->launches++;
+      if (rc != NIB_OK) return rc;
+    } else {
+      const NetBuffer& bi = net->bufs[op.fc_in];
+      int rc = launch_fc(bi.ptr, bi.C, net->bf16, (const float*)op.d_w, op.d_bias, N, op.fc_cin, op.fc_cout,
+                         d_logits, st);
+      net->launches++;
+      if (rc != NIB_OK) return rc;
+    }
+  }
+  return NIB_OK;
+}
+
+static int stage_input(nib_net* net, const void* d_x, int x_layout, int N, cudaStream_t st) {
+  const NetBuffer& bi = net->bufs[net->input_buf];
+  if (x_layout == NIB_IN_NCHW_F32) {
+    // the reference hands an N x C x H x W fp32 tensor (imagenet :245); channels beyond the model's
+    // real C are zero padding for the tensor-core path.
+    int C = bi.C;
+    // real channel count = Cin of the first conv reading this buffer
+    for (auto& op : net->ops)
+      if (op.kind == 0 && op.cd.in_buf == net->input_buf) { C = op.cd.Cin; break; }
+    int rc = launch_nchw_to_nhwc((const float*)d_x, N, C, bi.H, bi.W, bi.ptr, bi.C, bi.pad, net->bf16, st);
+    net->launches++;
+    return rc;
+  }
+  if (d_x != bi.ptr)
+    NIB_CUDA(cudaMemcpyAsync(bi.ptr, d_x, bi.elems_per_image * N * elem_size(net), cudaMemcpyDeviceToDevice, st));
+  return NIB_OK;
+}
+
+int nib_net_forward(nib_net* net, const void* d_x, int x_layout, int N, float* d_logits, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(net && net->finalized, "nib_net_forward: network not finalized");
+  NIB_REQUIRE(d_x && d_logits, "nib_net_forward: null pointer");
+  NIB_REQUIRE(N > 0 && N <= net->max_batch, "nib_net_forward: N=%d outside (0, max_batch=%d]", N, net->max_batch);
+  NIB_REQUIRE(x_layout == NIB_IN_NCHW_F32 || x_layout == NIB_IN_NATIVE, "nib_net_forward: bad x_layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!net->use_graph) {
+    int rc = stage_input(net, d_x, x_layout, N, st);
+    if (rc != NIB_OK) return rc;
+    return run_ops(net, N, d_logits, st);
+  }
+  nib_net::GraphKey key{N, x_layout, d_x, d_logits};
+  auto it = net->graphs.find(key);
+  if (it == net->graphs.end()) {
+    cudaStream_t cap;
+    NIB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    const long long l0 = net->launches, t0 = net->tc_launches;
+    NIB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int rc = stage_input(net, d_x, x_layout, N, cap);
+    if (rc == NIB_OK) rc = run_ops(net, N, d_logits, cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+    if (rc != NIB_OK || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cap);
+      if (rc == NIB_OK) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); rc = NIB_ECUDA; }
+      return rc;
+    }
+    nib_net::GraphVal val;
+    val.launches = net->launches - l0;
+    val.tc_launches = net->tc_launches - t0;
+    net->launches = l0;
+    net->tc_launches = t0;
+    NIB_CUDA(cudaGraphInstantiate(&val.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    it = net->graphs.insert({key, val}).first;
+  }
+  NIB_CUDA(cudaGraphLaunch(it->second.exec, st));
+  net->launches += it->second.launches;
+  net->tc_launches += it->second.tc_launches;
+  return NIB_OK;
+}
+
+int nib_net_forward_masked(nib_net* net, const nib_mask_args* args, float* d_logits, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(net && net->finalized && args, "nib_net_forward_masked: bad handle/args");
+  NIB_REQUIRE(args->N > 0 && args->N <= net->max_batch, "nib_net_forward_masked: N=%d outside (0, max_batch=%d]",
+              args->N, net->max_batch);
+  const NetBuffer& bi = net->bufs[net->input_buf];
+  NIB_REQUIRE(args->H == bi.H && args->W == bi.W && args->C <= bi.C, "nib_net_forward_masked: image %dx%dx%d does not match the network input %dx%dx%d",
+              args->C, args->H, args->W, bi.C, bi.H, bi.W);
+  nib_mask_args a = *args;
+  a.d_out = bi.ptr;
+  a.out_dtype = net->bf16 ? NIB_BF16 : NIB_F32;
+  a.layout = NIB_NHWC;
+  a.c_stride = bi.C;
+  a.pad_h = a.pad_w = bi.pad;
+  int rc = mask_synth_impl(&a, (cudaStream_t)stream);
+  net->launches += 1 + (bi.pad > 0) + (a.mode == NIB_MASK_REMOVE_MINMAX);
+  if (rc != NIB_OK) return rc;
+  return nib_net_forward(net, bi.ptr, NIB_IN_NATIVE, args->N, d_logits, stream);
+}
+
+int nib_net_buffer_info(nib_net* net, int buf, void** d_ptr, int* H, int* W, int* C, int* pad, int* dtype) {
+  NIB_REQUIRE(net && buf >= 0 && buf < (int)net->bufs.size(), "nib_net_buffer_info: bad buffer id");
+  const NetBuffer& b = net->bufs[buf];
+  if (d_ptr) *d_ptr = b.ptr;
+  if (H) *H = b.H;
+  if (W) *W = b.W;
+  if (C) *C = b.C;
+  if (pad) *pad = b.pad;
+  if (dtype) *dtype = net->bf16 ? NIB_BF16 : NIB_F32;
+  return NIB_OK;
+}
+
+int nib_net_read_buffer_nchw(nib_net* net, int buf, int N, float* d_out, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(net && buf >= 0 && buf < (int)net->bufs.size() && d_out, "nib_net_read_buffer_nchw: bad arguments");
+  NIB_REQUIRE(N > 0 && N <= net->max_batch, "nib_net_read_buffer_nchw: bad N");
+  const NetBuffer& b = net->bufs[buf];
+  return launch_nhwc_to_nchw(b.ptr, N, b.C, b.H, b.W, b.C, b.pad, net->bf16, d_out, (cudaStream_t)stream);
+}
+
+int nib_net_launch_counts(nib_net* net, long long* total, long long* tcgen05) {
+  NIB_REQUIRE(net != nullptr, "nib_net_launch_counts: null handle");
+  if (total) *total = net->launches;
+  if (tcgen05) *tcgen05 = net->tc_launches;
+  return NIB_OK;
+}
+
+int nib_net_set_tensor_core(nib_net* net, int enable) {
+  NIB_REQUIRE(net != nullptr, "nib_net_set_tensor_core: null handle");
+  net->use_tc = enable != 0;
+  for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
+  net->graphs.clear();
+  return NIB_OK;
+}
+
+int nib_net_set_graph(nib_net* net, int enable) {
+  NIB_REQUIRE(net != nullptr, "nib_net_set_graph: null handle");
+  net->use_graph = enable != 0;
+  return NIB_OK;
+}
+
+}  // extern "C"
