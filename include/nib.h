@@ -188,6 +188,13 @@ int nib_net_set_tensor_core(nib_net* net, int enable);
 /* 1 = replay forward through a CUDA graph per batch size (default 0) */
 int nib_net_set_graph(nib_net* net, int enable);
 
+/* Per-op device timing of one forward (CUDA events on `stream` around every launch; the input buffer must
+ * already hold N images, e.g. from a previous nib_net_forward_masked).  Arrays are host, length >= cap;
+ * *num_ops receives the op count.  h_kind: 0 SIMT conv, 1 tcgen05 conv, 2 pool, 3 fc.
+ * h_flops: 2*M*K*Cout for convs / fc (the algorithmic FLOPs SURVEY.md §8d counts), 0 for pools. */
+int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int cap,
+                    int* num_ops, void* stream);
+
 /* Scoring: top-1 index (first maximum, as torch .max(1)), softmax probability of `target`,
  * max softmax probability, and correct = (top1 == target).
  * imagenet :248,:257 ; bayesian_active_learning_imagenet.py:196-198 ; mnist :249-259.
@@ -243,13 +250,17 @@ int nib_gp_posterior(const double* d_L, int n, int ldl, const double* d_alpha,
 /* log marginal likelihood and d/d(log l) at the current factor (_gpr.py:588-655):
  *   lml = -0.5 y^T alpha - sum log L_ii - n/2 log 2pi
  *   grad = 0.5 * tr((alpha alpha^T - K^{-1}) dK/dtheta),  dK/dtheta = K_noisefree .* D2 / l^2
- * d_K0: noise-free Gram [n][ld]; d_D2: squared distances [n][ld] (fp64); d_Kinv: K^{-1} [n][ld]
- * Results to host doubles (synchronises the stream). */
+ * d_K0: noise-free Gram [n][ld]; d_Kinv: K^{-1} [n][ld]; squared distances are recomputed on the fly
+ * from the inputs (popcounts of d_Z for binary masks).  Results to host doubles (synchronises). */
 int nib_gp_lml(const double* d_L, int n, int ldl, const double* d_y, const double* d_alpha,
                double* h_lml, void* stream);
 int nib_gp_lml_grad(const double* d_K0, const double* d_Kinv, const double* d_alpha,
                     const uint64_t* d_Z, int words, int n, int ld, double length_scale,
                     double* h_grad, void* stream);
+/* same for real-valued inputs X [n,d] (the reference's 1-D firstIndex GP) */
+int nib_gp_lml_grad_rbf(const double* d_K0, const double* d_Kinv, const double* d_alpha,
+                        const double* d_X, int d, int n, int ld, double length_scale,
+                        double* h_grad, void* stream);
 
 /* Expected improvement, BayesianOptimization.py:37-54 (returns +EI; the reference returns -EI):
  *   s = greater_is_better ? 1 : -1;  Z = s*(mu-best)/sigma;  EI = s*(mu-best)*Phi(Z)+sigma*phi(Z)

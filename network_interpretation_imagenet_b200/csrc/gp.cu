@@ -420,6 +420,30 @@ lml_grad_kernel(const double* __restrict__ K0, const double* __restrict__ Kinv, 
     partial[i] = t;
   }
 }
+__global__ void __launch_bounds__(256)
+lml_grad_rbf_kernel(const double* __restrict__ K0, const double* __restrict__ Kinv, const double* __restrict__ alpha,
+                    const double* __restrict__ X, int d, int n, int ld, double inv_l, double* __restrict__ partial) {
+  const int i = blockIdx.x;
+  double acc = 0.0;
+  const double ai = alpha[i];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double s2 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double diff = X[(size_t)i * d + k] * inv_l - X[(size_t)j * d + k] * inv_l;
+      s2 += diff * diff;
+    }
+    acc = fma((ai * alpha[j] - Kinv[(size_t)i * ld + j]) * K0[(size_t)i * ld + j], s2, acc);
+  }
+  __shared__ double s[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) t += s[k];
+    partial[i] = t;
+  }
+}
 __global__ void sum_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
   __shared__ double s[32];
   double acc = 0.0;
@@ -598,6 +622,24 @@ int nib_gp_lml_grad(const double* d_K0, const double* d_Kinv, const double* d_al
   NIB_CUDA(cudaStreamSynchronize(st));
   // dK/dtheta = K0 .* D2 / l^2 ;  grad = 0.5 * sum((alpha alpha^T - K^-1) .* dK/dtheta)
   *h_grad = 0.5 * t / (length_scale * length_scale);
+  return NIB_OK;
+}
+
+int nib_gp_lml_grad_rbf(const double* d_K0, const double* d_Kinv, const double* d_alpha, const double* d_X, int d,
+                        int n, int ld, double length_scale, double* h_grad, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_K0 && d_Kinv && d_alpha && d_X && h_grad && n > 0 && d > 0 && ld >= n, "nib_gp_lml_grad_rbf: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_scratch((size_t)n + 16);
+  if (rc != NIB_OK) return rc;
+  lml_grad_rbf_kernel<<<n, 256, 0, st>>>(d_K0, d_Kinv, d_alpha, d_X, d, n, ld, 1.0 / length_scale, g_scratch + 16);
+  NIB_LAUNCH_CHECK();
+  sum_kernel<<<1, 1024, 0, st>>>(g_scratch + 16, n, g_scratch);
+  NIB_LAUNCH_CHECK();
+  double t = 0.0;
+  NIB_CUDA(cudaMemcpyAsync(&t, g_scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
+  NIB_CUDA(cudaStreamSynchronize(st));
+  *h_grad = 0.5 * t;  // D2 here is already sqeuclidean(X / l): dK/dtheta = K0 .* D2
   return NIB_OK;
 }
 

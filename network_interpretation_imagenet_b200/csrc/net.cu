@@ -382,6 +382,52 @@ int nib_net_forward(nib_net* net, const void* d_x, int x_layout, int N, float* d
   return NIB_OK;
 }
 
+int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int cap, int* num_ops,
+                    void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(net && net->finalized && h_ms && h_kind && h_flops && num_ops, "nib_net_profile: bad arguments");
+  NIB_REQUIRE(N > 0 && N <= net->max_batch, "nib_net_profile: bad N");
+  const int nops = (int)net->ops.size();
+  NIB_REQUIRE(cap >= nops, "nib_net_profile: cap=%d < %d ops", cap, nops);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(nops + 1);
+  for (auto& e : ev) NIB_CUDA(cudaEventCreate(&e));
+  float* d_logits = nullptr;
+  NIB_CUDA(cudaMalloc(&d_logits, sizeof(float) * (size_t)N * (net->num_classes > 0 ? net->num_classes : 1)));
+  // run op by op, reusing run_ops on single-op slices
+  std::vector<NetOp> all;
+  all.swap(net->ops);
+  int rc = NIB_OK;
+  for (int i = 0; i < nops && rc == NIB_OK; ++i) {
+    cudaEventRecord(ev[i], st);
+    net->ops.assign(1, all[i]);
+    rc = run_ops(net, N, d_logits, st);
+  }
+  cudaEventRecord(ev[nops], st);
+  net->ops.swap(all);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (rc == NIB_OK && ce != cudaSuccess) { set_error("nib_net_profile: %s", cudaGetErrorString(ce)); rc = NIB_ECUDA; }
+  for (int i = 0; i < nops && rc == NIB_OK; ++i) {
+    cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+    const NetOp& op = net->ops[i];
+    if (op.kind == 0) {
+      const NetBuffer& bo = net->bufs[op.cd.out_buf];
+      h_kind[i] = (op.plan && net->use_tc) ? 1 : 0;
+      h_flops[i] = 2.0 * N * bo.H * bo.W * (double)op.cd.R * op.cd.S * op.cd.Cin * op.cd.Cout;
+    } else if (op.kind == 1) {
+      h_kind[i] = 2;
+      h_flops[i] = 0.0;
+    } else {
+      h_kind[i] = 3;
+      h_flops[i] = 2.0 * N * (double)op.fc_cin * op.fc_cout;
+    }
+  }
+  *num_ops = nops;
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaFree(d_logits);
+  return rc;
+}
+
 int nib_net_forward_masked(nib_net* net, const nib_mask_args* args, float* d_logits, void* stream) {
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(net && net->finalized && args, "nib_net_forward_masked: bad handle/args");

@@ -1,0 +1,81 @@
+"""The whole hot path behind one object: masks -> classifier -> scores (-> GP), sharded over ranks.
+
+Replaces the body of the reference's hot loops (generate_gp_training_data_imagenet.py:221-266,
+generate_gp_training_data_mnist.py:203-269, generate_gp_training_data_cifar.py:307-342,
+bayesian_active_learning_imagenet.py:178-198): instead of one mask, one H2D copy, one batch-1 forward and
+one device sync per iteration, all N masks of an image are synthesised and scored in micro-batches on the
+device, and each rank of a torch.distributed job scores a contiguous slice of the masks (masks are
+independent work units); one all-gather of (target_prob, top1) per call is the only
+collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .classifier import Classifier
+from .masks import KEEP_MUL, REMOVE_MINMAX, MaskSynth
+from .scoring import score
+
+
+def shard_range(N: int, rank: int, world: int) -> tuple[int, int, int]:
+    """Contiguous slice [lo, hi) of N masks for `rank`, and the padded per-rank length (equal on all ranks so a
+    single all_gather_into_tensor works).  Mask order is global, so results are identical to a 1-GPU run."""
+    per = (N + world - 1) // world
+    lo = min(N, rank * per)
+    hi = min(N, lo + per)
+    return lo, hi, per
+
+
+def gather_scores(local: torch.Tensor, N: int, group=None) -> torch.Tensor:
+    """All-gather a [per, F] per-rank score block into the global [N, F] table (works on gloo/CPU and nccl/CUDA)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local[:N]
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out[:N]
+
+
+class PerturbationEngine:
+    def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
+                 max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False):
+        _lib.load()
+        self.device = torch.device(device)
+        self.target = int(target)
+        self.mode = mode
+        self.group = group
+        self.synth = MaskSynth(image, segments, S=S, device=device)
+        self.classifier = model if isinstance(model, Classifier) else Classifier.from_torch(
+            model, (self.synth.H, self.synth.W), precision=precision, max_batch=max_batch)
+        if use_graph:
+            self.classifier.set_graph(True)
+        self.rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def score_local(self, sel_bits, out: torch.Tensor | None = None):
+        """Scores for the given selections on this rank only.  Returns [n, 2] fp32: (target_prob, top1)."""
+        d_sel = self.synth.device_bits(sel_bits)
+        n = int(d_sel.shape[0])
+        if out is None:
+            out = torch.zeros(n, 2, dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        logits = self.classifier.forward_masked(self.synth, d_sel, self.mode)
+        s = score(logits, self.target)
+        out[:n, 0] = s["target_prob"]
+        out[:n, 1] = s["top1"].to(torch.float32)   # class ids < 2^24 are exact in fp32
+        return out
+
+    def score_masks(self, sel_bits) -> dict:
+        """All N masks, sharded over the ranks of `group`; every rank returns the full tables."""
+        bits = np.ascontiguousarray(sel_bits, dtype=np.uint64)
+        N = bits.shape[0]
+        lo, hi, per = shard_range(N, self.rank, self.world)
+        local = torch.zeros(per, 2, dtype=torch.float32, device=self.device)
+        self.score_local(bits[lo:hi], out=local)
+        table = gather_scores(local, N, self.group)
+        top1 = table[:, 1].to(torch.int32)
+        return {"target_prob": table[:, 0], "top1": top1, "correct": (top1 == self.target)}

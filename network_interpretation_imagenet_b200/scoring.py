@@ -1,0 +1,30 @@
+"""Stage 2 tail host mirror: logits -> (top-1, target-class probability, max probability, correct).
+
+`output.data.max(1, keepdim=True)[1]` (generate_gp_training_data_imagenet.py:248),
+`F.softmax(mask_output)[0][label]` (bayesian_active_learning_imagenet.py:196-198),
+`F.softmax(pred0, dim=1).max(1)` (generate_gp_training_data_mnist.py:250-256).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def score(logits: torch.Tensor, target: int, out=None):
+    """logits [N,K] fp32 cuda.  Returns dict(top1 int32[N], target_prob f32[N], max_prob f32[N], correct u8[N]).
+    `out` may hold preallocated tensors under the same keys (e.g. slices of an all-gather buffer)."""
+    lib = _lib.load()
+    if not logits.is_cuda or logits.dtype != torch.float32 or not logits.is_contiguous():
+        raise ValueError("logits must be a contiguous fp32 CUDA tensor")
+    N, K = (int(v) for v in logits.shape)
+    out = dict(out or {})
+    dev = logits.device
+    out.setdefault("top1", torch.empty(N, dtype=torch.int32, device=dev))
+    out.setdefault("target_prob", torch.empty(N, dtype=torch.float32, device=dev))
+    out.setdefault("max_prob", torch.empty(N, dtype=torch.float32, device=dev))
+    out.setdefault("correct", torch.empty(N, dtype=torch.uint8, device=dev))
+    _lib.check(lib.nib_score(logits.data_ptr(), N, K, int(target), out["top1"].data_ptr(),
+                             out["target_prob"].data_ptr(), out["max_prob"].data_ptr(), out["correct"].data_ptr(),
+                             _lib.stream_handle()), "nib_score")
+    return out

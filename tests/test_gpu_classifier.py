@@ -1,0 +1,241 @@
+"""GPU: stage 2 (classifier forward + scoring) through the C ABI.
+
+Floating-point kernels: compared with the oracle's torch fp32 CPU forward (the reference's `model(x)`,
+generate_gp_training_data_imagenet.py:246).  Tolerances are north_star's: <= 1e-4 (fp32 mode), <= 1e-2 (bf16 mode),
+measured as max|a-b| / max|b| over the logits of a batch, plus identical top-1 on every input."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import classifier as ocls
+from oracle import scoring as oscore
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4
+TOL_BF16 = 1e-2
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ---- tcgen05 GEMM descriptors ---------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (300, 256, 256), (1000, 32, 576), (4096, 128, 1024)])
+def test_tc_gemm(nib, M, N, K):
+    lib = nib._lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    B = (torch.randn(N, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    Cd = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    nib._lib.check(lib.nib_tc_gemm_bf16(A.data_ptr(), B.data_ptr(), Cd.data_ptr(), M, N, K, nib._lib.stream_handle()),
+                   "nib_tc_gemm_bf16")
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    err = (Cd - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+# ---- single convolutions through a one-layer network -------------------------------------------------
+def _one_conv_net(nib, precision, Cin, Cout, k, stride, pad, H, W, relu, residual, N, seed, tensor_core=True):
+    from network_interpretation_imagenet_b200 import _lib
+    from network_interpretation_imagenet_b200.classifier import _Builder, Classifier, _out_hw
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    x = torch.randn(N, Cin, H, W, generator=g)
+    b = _Builder({"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision], N)
+    x_in = b.buffer(H, W, Cin, pooled=False)
+    Ho, Wo = _out_hw(H, k, stride, pad), _out_hw(W, k, stride, pad)
+    res_buf = None
+    xin2 = x_in
+    if residual:   # residual = a 1x1 stride-matched projection of the input computed first (same engine, SIMT-checked separately)
+        res_buf = b.buffer(Ho, Wo, Cout, pooled=False)
+        wr = torch.randn(Cout, Cin, 1, 1, generator=g) / np.sqrt(Cin)
+        b.conv(x_in, Cin, res_buf, Cout, wr, None, 1, stride, 0, relu=False)
+    out = b.buffer(Ho, Wo, Cout, pooled=False)
+    b.conv(xin2, Cin, out, Cout, w, bias, k, stride, pad, relu=relu, res=res_buf, res_C=Cout if residual else 0)
+    feat = b.buffer(1, 1, Cout)
+    if Ho == Wo:
+        b.pool(_lib.POOL_AVG, out, Cout, feat, Ho, Ho, 0)
+    b.fc(feat, Cout, 4, torch.zeros(4, Cout), None)
+    net = Classifier(b, x_in, (Cin, H, W), 4, precision, N, taps={"out": out, "res": res_buf})
+    net.set_tensor_core(tensor_core)
+    net.forward(x.cuda())
+    got = net.read_tap("out", N).cpu()
+    if precision == "bf16":
+        xr, wq = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    else:
+        xr, wq = x, w
+    ref = F.conv2d(xr.double(), wq.double(), bias.double(), stride=stride, padding=pad)
+    if residual:
+        wrq = wr.to(torch.bfloat16).float() if precision == "bf16" else wr
+        r = F.conv2d(xr.double(), wrq.double(), None, stride=stride)
+        if precision == "bf16":
+            r = r.float().to(torch.bfloat16).double()
+        ref = ref + r
+    if relu:
+        ref = ref.clamp_min(0)
+    return got.double(), ref, net
+
+
+CONV_CASES = [
+    # Cin, Cout, k, stride, pad, H,  W,  relu, residual
+    (64, 64, 1, 1, 0, 16, 16, True, False),
+    (64, 256, 1, 1, 0, 14, 14, False, True),
+    (256, 64, 1, 1, 0, 14, 14, True, False),
+    (64, 64, 3, 1, 1, 16, 16, True, False),
+    (128, 128, 3, 1, 1, 14, 14, True, False),
+    (128, 128, 3, 2, 1, 28, 28, True, False),
+    (256, 512, 1, 2, 0, 28, 28, False, False),
+    (128, 32, 3, 1, 1, 7, 7, False, False),
+    (512, 512, 3, 1, 1, 7, 7, True, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "cin%d_cout%d_k%d_s%d_h%d" % (c[0], c[1], c[2], c[3], c[5]))
+def test_conv_tcgen05_vs_torch(nib, case):
+    Cin, Cout, k, stride, pad, H, W, relu, residual = case
+    got, ref, net = _one_conv_net(nib, "bf16", Cin, Cout, k, stride, pad, H, W, relu, residual, N=5, seed=sum(case[:7]))
+    total, tc = net.launch_counts()
+    assert tc >= 1, "the tcgen05 path did not run for an eligible layer"
+    err = (got - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    assert err <= 1.2e-2 * scale, f"max abs err {err} (scale {scale})"   # bf16 output rounding = 2^-9 rel + accum
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", [(3, 64, 7, 2, 3, 32, 32, True, False), (16, 32, 3, 2, 1, 16, 16, True, False),
+                                  (64, 128, 3, 1, 1, 9, 9, False, True), (1, 32, 3, 1, 1, 28, 28, True, False)],
+                         ids=lambda c: "cin%d_cout%d_k%d_s%d" % (c[0], c[1], c[2], c[3]))
+def test_conv_simt_vs_torch(nib, precision, case):
+    Cin, Cout, k, stride, pad, H, W, relu, residual = case
+    got, ref, net = _one_conv_net(nib, precision, Cin, Cout, k, stride, pad, H, W, relu, residual, N=3,
+                                  seed=sum(case[:7]), tensor_core=False)
+    err = (got - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    assert err <= (1e-5 if precision == "fp32" else 1.2e-2) * scale
+
+
+# ---- whole networks ------------------------------------------------------------------------------------
+def _check_net(nib, model, x, precision, tol, max_batch=None):
+    want = ocls.forward_logits(model, x).numpy()
+    net = nib.Classifier.from_torch(model, tuple(x.shape[2:]), precision=precision, max_batch=max_batch or x.shape[0])
+    got = net.forward(torch.as_tensor(x).cuda()).cpu().numpy()
+    err = rel_err(got, want)
+    assert err <= tol, f"{precision}: rel err {err:.3e} > {tol}"
+    assert np.array_equal(got.argmax(1), want.argmax(1)), "top-1 differs"
+    return net, got, want
+
+
+def test_mnist_net_fp32_with_taps(nib):
+    m = ocls.load_mnist_net()
+    x = torch.rand(16, 1, 28, 28, generator=torch.Generator().manual_seed(3))
+    net, got, want = _check_net(nib, m, x, "fp32", TOL_FP32)
+    with torch.no_grad():
+        x0, x1, x2, _ = m(x)
+    for name, ref in (("x0", x0), ("x1", x1), ("x2", x2)):
+        tap = net.read_tap(name, 16).cpu().numpy()
+        assert rel_err(tap, ref.numpy()) <= TOL_FP32, name
+
+
+def test_mnist_net_bf16(nib):
+    m = ocls.load_mnist_net()
+    x = torch.rand(64, 1, 28, 28, generator=torch.Generator().manual_seed(4))
+    _check_net(nib, m, x, "bf16", TOL_BF16)
+
+
+def test_resnet56_fp32_checkpoint_and_golden(nib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "resnet56.npz"))
+    m = ocls.load_resnet56()
+    net = nib.Classifier.from_torch(m, (32, 32), precision="fp32", max_batch=4)
+    got = net.forward(torch.from_numpy(g["x"]).cuda()).cpu().numpy()
+    assert rel_err(got, g["logits"]) <= TOL_FP32          # the reference's own module output
+    x = torch.rand(32, 3, 32, 32, generator=torch.Generator().manual_seed(9))
+    _check_net(nib, m, x, "fp32", TOL_FP32, max_batch=16)  # also exercises chunking over max_batch
+
+
+def test_resnet56_bf16(nib):
+    m = ocls.load_resnet56()
+    x = torch.rand(64, 3, 32, 32, generator=torch.Generator().manual_seed(10))
+    want = ocls.forward_logits(m, x).numpy()
+    net = nib.Classifier.from_torch(m, (32, 32), precision="bf16", max_batch=64)
+    got = net.forward(x.cuda()).cpu().numpy()
+    assert rel_err(got, want) <= 2e-2    # 55 sequential bf16 layers; top-1 is the contract that matters
+    margin = np.sort(want, 1)[:, -1] - np.sort(want, 1)[:, -2]
+    safe = margin > 0.05 * np.abs(want).max()
+    assert np.array_equal(got.argmax(1)[safe], want.argmax(1)[safe])
+
+
+def test_resnet101_fp32(nib):
+    m = ocls.build_imagenet_model("resnet101")
+    x = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(2, 1, 1, 1)
+    x[1] = x[1].flip(2) * 0.5
+    _check_net(nib, m, x, "fp32", TOL_FP32)
+
+
+def test_resnet101_bf16_tcgen05(nib):
+    m = ocls.build_imagenet_model("resnet101")
+    g = torch.Generator().manual_seed(2)
+    base = torch.from_numpy(synthetic.synthetic_image("imagenet"))
+    x = base[None] * (torch.rand(8, 1, 224, 224, generator=g) > 0.4).float()
+    net, got, want = _check_net(nib, m, x, "bf16", TOL_BF16)
+    total, tc = net.launch_counts()
+    assert tc >= 100, f"only {tc} tcgen05 launches for ResNet-101 (expected 103 convs on the tensor path)"
+
+
+def test_densenet121_fp32(nib):
+    m = ocls.build_imagenet_model("densenet121")
+    x = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(2, 1, 1, 1)
+    x[1] = x[1].flip(1)
+    _check_net(nib, m, x, "fp32", TOL_FP32)
+
+
+def test_densenet121_bf16(nib):
+    m = ocls.build_imagenet_model("densenet121")
+    x = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(4, 1, 1, 1)
+    x = x * torch.rand(4, 1, 1, 1, generator=torch.Generator().manual_seed(1))
+    _check_net(nib, m, x, "bf16", TOL_BF16)
+
+
+def test_densenet_cifar_fp32(nib):
+    torch.manual_seed(5)
+    m = ocls.DenseNetCifar(depth=22, growth_rate=12, num_init_features=24, bn_size=4).eval()
+    ocls._randomize_bn(m, 6)
+    x = torch.rand(8, 3, 32, 32, generator=torch.Generator().manual_seed(7))
+    _check_net(nib, m, x, "fp32", TOL_FP32)
+
+
+def test_graph_replay_matches_eager(nib):
+    m = ocls.load_resnet56()
+    x = torch.rand(8, 3, 32, 32, generator=torch.Generator().manual_seed(12)).cuda()
+    net = nib.Classifier.from_torch(m, (32, 32), precision="fp32", max_batch=8)
+    a = net.forward(x).clone()
+    net.set_graph(True)
+    out = torch.empty_like(a)
+    b1 = net.forward(x, out=out).clone()
+    b2 = net.forward(x, out=out).clone()
+    assert torch.equal(a, b1) and torch.equal(a, b2)
+
+
+# ---- scoring --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K", [(1, 10), (257, 1000), (64, 10), (5, 1001)])
+def test_score_vs_oracle(nib, N, K):
+    g = torch.Generator().manual_seed(N * K)
+    logits = torch.randn(N, K, generator=g) * 3
+    logits[0, K // 2] = logits[0].max() + 1
+    if N > 1:
+        logits[1, 3] = logits[1, 7] = logits[1].max() + 2   # a tie: torch.max returns the first index
+    target = 3
+    top1, tp, mp, corr = oscore.score(logits, target)
+    s = nib.score(logits.cuda(), target)
+    assert np.array_equal(s["top1"].cpu().numpy(), top1)
+    assert np.array_equal(s["correct"].cpu().numpy(), corr)
+    np.testing.assert_allclose(s["target_prob"].cpu().numpy(), tp, rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(s["max_prob"].cpu().numpy(), mp, rtol=2e-5, atol=1e-9)
