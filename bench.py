@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-gp", action="store_true")
     ap.add_argument("--gp-n", type=int, default=4096)
     ap.add_argument("--graph", action="store_true", help="replay each micro-batch forward as a CUDA graph")
+    ap.add_argument("--profile-json", default=None, help="write the per-op CUDA-event profile of one micro-batch here")
     return ap.parse_args()
 
 
@@ -293,6 +294,13 @@ def run_ours(args):
     if rank == 0:
         clf.forward_masked(synth, my_bits_dev[:mb], nib.KEEP_MUL, out=logits[:min(mb, per)])
         prof = [clf.profile(min(mb, per)) for _ in range(3)][-1]
+        if args.profile_json:
+            with open(args.profile_json, "w") as f:
+                json.dump({"micro_batch": min(mb, per), "ops": [
+                    {"ms": p[0], "kind": ["simt_conv", "tc_conv", "pool", "fc"][p[1]], "gflop": p[2] / 1e9,
+                     "tflops": (p[2] / (p[0] / 1e3) / 1e12) if p[0] > 0 else None,
+                     "Hout": p[3][0], "Wout": p[3][1], "Cin": p[3][2], "Cout": p[3][3], "k": p[3][4], "stride": p[3][5],
+                     "residual": p[3][6], "block_n": p[3][7]} for p in prof]}, f, indent=0)
         tc_ms = sum(p[0] for p in prof if p[1] == 1)
         tc_fl = sum(p[2] for p in prof if p[1] == 1)
         all_ms = sum(p[0] for p in prof)

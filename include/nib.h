@@ -191,16 +191,20 @@ int nib_net_set_graph(nib_net* net, int enable);
 /* Per-op device timing of one forward (CUDA events on `stream` around every launch; the input buffer must
  * already hold N images, e.g. from a previous nib_net_forward_masked).  Arrays are host, length >= cap;
  * *num_ops receives the op count.  h_kind: 0 SIMT conv, 1 tcgen05 conv, 2 pool, 3 fc.
- * h_flops: 2*M*K*Cout for convs / fc (the algorithmic FLOPs SURVEY.md §8d counts), 0 for pools. */
-int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int cap,
-                    int* num_ops, void* stream);
+ * h_flops: 2*M*K*Cout for convs / fc (the algorithmic FLOPs SURVEY.md §8d counts), 0 for pools.
+ * h_geom (optional, 8 ints per op): Hout, Wout, Cin, Cout, R, stride, has_residual, block_n. */
+int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int* h_geom,
+                    int cap, int* num_ops, void* stream);
 
 /* Scoring: top-1 index (first maximum, as torch .max(1)), softmax probability of `target`,
  * max softmax probability, and correct = (top1 == target).
  * imagenet :248,:257 ; bayesian_active_learning_imagenet.py:196-198 ; mnist :249-259.
- * Any output pointer may be NULL. */
+ * d_margin: (top1 logit - runner-up logit) / max|logit| per row — the tie detector of the bf16 path: rows whose
+ * relative margin is inside the bf16 logit tolerance are re-scored in fp32 by the host mirror so that top-1 is
+ * identical to the reference's on every mask.  Any output pointer may be NULL. */
 int nib_score(const float* d_logits, int N, int K, int target, int32_t* d_top1,
-              float* d_target_prob, float* d_max_prob, uint8_t* d_correct, void* stream);
+              float* d_target_prob, float* d_max_prob, uint8_t* d_correct, float* d_margin,
+              void* stream);
 
 /* Standalone tcgen05 GEMM self-test hook: C[M,N] = A[M,K] * B[N,K]^T (bf16 in, fp32 out).
  * Used by tests to validate descriptors independent of the network executor. */

@@ -74,8 +74,8 @@ _PROTOTYPES = {
     "nib_net_launch_counts": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "nib_net_set_tensor_core": (_i, [_vp, _i]),
     "nib_net_set_graph": (_i, [_vp, _i]),
-    "nib_net_profile": (_i, [_vp, _i, _vp, _vp, _vp, _i, C.POINTER(_i), _vp]),
-    "nib_score": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "nib_net_profile": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(_i), _vp]),
+    "nib_score": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nib_tc_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "nib_gp_gram_binary": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _vp, _i, _vp]),
     "nib_gp_gram_rbf": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _i, _vp, _i, _vp]),

@@ -204,10 +204,11 @@ class Classifier:
         ms = (C.c_float * cap)()
         kind = (C.c_int * cap)()
         flops = (C.c_double * cap)()
+        geom = (C.c_int * (8 * cap))()
         n = C.c_int()
-        _lib.check(self.lib.nib_net_profile(self.h, N, ms, kind, flops, cap, C.byref(n), _lib.stream_handle()),
+        _lib.check(self.lib.nib_net_profile(self.h, N, ms, kind, flops, geom, cap, C.byref(n), _lib.stream_handle()),
                    "nib_net_profile")
-        return [(ms[i], kind[i], flops[i]) for i in range(n.value)]
+        return [(ms[i], kind[i], flops[i], tuple(geom[8 * i:8 * i + 8])) for i in range(n.value)]
 
     def read_tap(self, name: str, N: int) -> torch.Tensor:
         """NCHW fp32 copy of a named intermediate (MNIST x0/x1/x2, mnist :97-105) for the last batch."""
@@ -230,8 +231,11 @@ def _lower_tv_resnet(m, hw, prec, precision, max_batch):
     H, W = hw
     b = _Builder(prec, max_batch)
     cin = m.conv1.in_channels
-    x_in = b.buffer(H, W, _in_cpad(cin), pooled=False)
     c1 = m.conv1
+    stem_tc = (precision == "bf16" and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3) and cin <= 8)
+    # tcgen05 stem: 8-channel-padded pixels (16 B) inside a 3-pixel zero halo, so each filter row of an output pixel
+    # is one contiguous 128 B window (conv_tc.cu tc_conv_is_stem)
+    x_in = b.buffer(H, W, 8, pad=3, pooled=False) if stem_tc else b.buffer(H, W, _in_cpad(cin), pooled=False)
     Hc, Wc = _out_hw(H, c1.kernel_size[0], c1.stride[0], c1.padding[0]), _out_hw(W, c1.kernel_size[0], c1.stride[0], c1.padding[0])
     t = b.buffer(Hc, Wc, c1.out_channels)
     w, bias = fold_bn(c1.weight, c1.bias, m.bn1)
@@ -380,8 +384,9 @@ def _lower_tv_densenet(m, hw, prec, precision, max_batch):
     H, W = hw
     f = m.features
     b = _Builder(prec, max_batch)
-    x_in = b.buffer(H, W, _in_cpad(3), pooled=False)
     c0 = f.conv0
+    stem_tc = (precision == "bf16" and c0.kernel_size == (7, 7) and c0.stride == (2, 2) and c0.padding == (3, 3))
+    x_in = b.buffer(H, W, 8, pad=3, pooled=False) if stem_tc else b.buffer(H, W, _in_cpad(3), pooled=False)
     Hc, Wc = _out_hw(H, 7, 2, 3), _out_hw(W, 7, 2, 3)
     t = b.buffer(Hc, Wc, c0.out_channels)
     w, bias = fold_bn(c0.weight, None, f.norm0)

@@ -217,7 +217,64 @@ __global__ void pool_kernel(PoolParams p) {
   Elem<T>::st(out + (((size_t)n * p.P + pp) * p.Q + q) * p.out_cstride + p.out_coff + c, acc);
 }
 
+// 8 bf16 channels (one 128-bit load/store) per thread; no pre-activation.
+__global__ void __launch_bounds__(256)
+pool_bf16x8_kernel(PoolParams p) {
+  const __nv_bfloat16* __restrict__ in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+  __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int C8 = p.C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)p.N * p.P * p.Q * C8;
+  if (idx >= total) return;
+  const int c = (int)(idx % C8) * 8;
+  long long t = idx / C8;
+  const int q = (int)(t % p.Q); t /= p.Q;
+  const int pp = (int)(t % p.P);
+  const int n = (int)(t / p.P);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = p.kind == NIB_POOL_MAX ? -INFINITY : 0.f;
+  for (int r = 0; r < p.k; ++r) {
+    const int ih = pp * p.stride - p.pad + r;
+    if (ih < 0 || ih >= p.Hin) continue;
+    for (int s = 0; s < p.k; ++s) {
+      const int iw = q * p.stride - p.pad + s;
+      if (iw < 0 || iw >= p.Win) continue;
+      const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * p.Hin + ih) * p.Win + iw) * p.in_cstride + p.in_coff + c);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        if (p.kind == NIB_POOL_MAX) {
+          acc[2 * j] = fmaxf(acc[2 * j], f.x);
+          acc[2 * j + 1] = fmaxf(acc[2 * j + 1], f.y);
+        } else {
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    }
+  }
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = acc[2 * j], b = acc[2 * j + 1];
+    if (p.kind == NIB_POOL_AVG) { a = a / (float)(p.k * p.k); b = b / (float)(p.k * p.k); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    ow[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)n * p.P + pp) * p.Q + q) * p.out_cstride + p.out_coff + c) = o;
+}
+
 int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st) {
+  if (bf16 && p.pre_scale == nullptr && p.C % 8 == 0 && p.in_cstride % 8 == 0 && p.in_coff % 8 == 0 &&
+      p.out_cstride % 8 == 0 && p.out_coff % 8 == 0) {
+    long long total8 = (long long)p.N * p.P * p.Q * (p.C / 8);
+    pool_bf16x8_kernel<<<(unsigned)ceil_div_ll(total8, 256), 256, 0, st>>>(p);
+    NIB_LAUNCH_CHECK();
+    return NIB_OK;
+  }
   long long total = (long long)p.N * p.P * p.Q * p.C;
   unsigned blocks = (unsigned)ceil_div_ll(total, 256);
   if (bf16)

@@ -45,7 +45,9 @@ struct TcKernelParams {
   int num_k_blocks;
   int cblocks;      // Cin / 64
   int S;            // filter width (tap -> (r, s))
-  int im2col;       // 0: tiled 2D A map, 1: im2col 4D A map
+  int im2col;       // 0: tiled 2D A map, 1: im2col 4D A map, 2: stem rows (overlapping-window 4D tiled map)
+  int tile_rows;    // valid output rows per M tile (128; Q for the stem mode: one output row per tile)
+  int a_bytes;      // bytes the A load delivers per stage (tile_rows * 128)
   int P, Q, stride, pad;
   int in_coff;
   int n_tiles;      // ceil(Cout / BLOCK_N)
@@ -96,6 +98,13 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
       "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
@@ -178,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x % p.n_tiles;
   const int m_tile = blockIdx.x / p.n_tiles;
-  const int m0 = m_tile * TC_BLOCK_M;
+  const int m0 = m_tile * p.tile_rows;
   const int n0 = n_tile * BLOCK_N;
 
   if (warp == 0 && lane == 0) {
@@ -206,13 +215,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ===== TMA producer =====
       int w0 = 0, h0 = 0, img = 0;
-      if (p.im2col) {
+      if (p.im2col == 1) {
         const int pq = p.P * p.Q;
         img = m0 / pq;
         const int rem = m0 - img * pq;
         const int pp = rem / p.Q, qq = rem - pp * p.Q;
         w0 = qq * p.stride - p.pad;
         h0 = pp * p.stride - p.pad;
+      } else if (p.im2col == 2) {   // one output row (img, pp) per tile; input rows pp*stride + r of the haloed image
+        img = m_tile / p.P;
+        h0 = (m_tile - img * p.P) * p.stride;
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -220,12 +232,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
         const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
         const uint32_t b_dst = a_dst + SM::A_BYTES;
-        mbar_arrive_expect_tx(full_bar(stage), SM::STAGE_BYTES);
+        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + SM::B_BYTES));
         const int tap = kb / p.cblocks;
         const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
-        if (p.im2col) {
+        if (p.im2col == 1) {
           const int r = tap / p.S, s = tap - r * p.S;
           tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+        } else if (p.im2col == 2) {
+          tma_load_4d(a_dst, &tmA, full_bar(stage), 0, 0, h0 + kb, img);   // k-block kb = filter row r
         } else {
           tma_load_2d(a_dst, &tmA, full_bar(stage), c0, m0);
         }
@@ -261,8 +275,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;
     mbar_wait(tmem_full_bar, 0, p.err_flag, 3);
     tc_fence_after();
-    const int row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < p.M;
+    const int lrow = quarter * 32 + lane;
+    const int row = m0 + lrow;
+    const bool row_ok = row < p.M && lrow < p.tile_rows;
 #pragma unroll 1
     for (int cc = 0; cc < BLOCK_N; cc += 32) {
       uint32_t v[32];
@@ -359,6 +374,7 @@ struct TcConvPlan {
   CUtensorMap tmA, tmB;
   int block_n, stages;
   int im2col;
+  int tile_rows;
   int num_k_blocks, cblocks;
   unsigned int* err_flag;
 };
@@ -383,7 +399,19 @@ static int encode_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t inner, uint
   return NIB_OK;
 }
 
+// 7x7 stride-2 pad-3 stem on a haloed, 8-channel-padded NHWC input (torchvision conv1): for filter row r the 7 taps x 8
+// channels of output pixel q are 56 contiguous elements starting at pixel 2q of input row 2p+r, so a tiled map whose
+// pixel dimension advances 2 pixels (32 B) per index delivers a [Q x 64] K-major tile per filter row (8 zero-weight
+// filler elements).  K = 7 x 64.
+bool tc_conv_is_stem(const ConvParams& p) {
+  return p.R == 7 && p.S == 7 && p.stride == 2 && p.pad == 3 && p.Cin <= 8 && p.in_cstride == 8 && p.in_coff == 0 &&
+         p.in_halo == 3 && p.Cout % 32 == 0 && p.Q <= TC_BLOCK_M && p.out_halo == 0 && p.out_cstride % 8 == 0 &&
+         p.out_coff % 8 == 0 && p.pre_scale == nullptr && p.res == nullptr && p.w_alt != nullptr &&
+         (p.Win + 2 * p.in_halo) >= 2 * (p.Q - 1) + 8;
+}
+
 bool tc_conv_supported(const ConvParams& p) {
+  if (tc_conv_is_stem(p)) return true;
   if (p.Cin % TC_BLOCK_K != 0) return false;
   if (p.in_cstride % 8 != 0 || p.in_coff % 8 != 0) return false;   // 16 B TMA alignment
   if (p.Cout % 32 != 0) return false;
@@ -418,6 +446,30 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
   memset(plan, 0, sizeof(*plan));
   plan->err_flag = g_err_flag;
   plan->block_n = pick_block_n(p.Cout);
+  plan->tile_rows = TC_BLOCK_M;
+  if (tc_conv_is_stem(p)) {
+    plan->im2col = 2;
+    plan->cblocks = 1;
+    plan->num_k_blocks = 7;
+    plan->tile_rows = p.Q;
+    rc = encode_2d_bf16(&plan->tmB, p.w_alt, 7 * 64, (uint64_t)p.Cout, 7 * 64 * 2, TC_BLOCK_K, plan->block_n);
+    if (rc != NIB_OK) { delete plan; return rc; }
+    const int Hp = p.Hin + 6, Wp = p.Win + 6;
+    cuuint64_t dims[4] = {64, (cuuint64_t)p.Q, (cuuint64_t)Hp, (cuuint64_t)max_batch};
+    cuuint64_t strides[3] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16};   // 2 pixels, one row, one image
+    cuuint32_t box[4] = {64, (cuuint32_t)p.Q, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeTiled(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides,
+                               box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (stem, overlapping windows) failed (%d)", (int)r);
+      delete plan;
+      return NIB_ECUDA;
+    }
+    *out = plan;
+    return NIB_OK;
+  }
   plan->cblocks = p.Cin / TC_BLOCK_K;
   plan->num_k_blocks = p.R * p.S * plan->cblocks;
   plan->im2col = !(p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0);
@@ -459,6 +511,7 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
 }
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+int tc_conv_plan_block_n(const TcConvPlan* plan) { return plan->block_n; }
 
 template <int BLOCK_N, int STAGES>
 static int launch_tc(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
@@ -510,7 +563,9 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.in_coff = p.in_coff;
   kp.n_tiles = ceil_div(p.Cout, plan->block_n);
   kp.err_flag = plan->err_flag;
-  const int tiles = ceil_div(p.M, TC_BLOCK_M) * kp.n_tiles;
+  kp.tile_rows = plan->tile_rows;
+  kp.a_bytes = plan->tile_rows * TC_BLOCK_K * 2;
+  const int tiles = ceil_div(p.M, plan->tile_rows) * kp.n_tiles;
   return tc_dispatch(plan, kp, tiles, st);
 }
 
@@ -551,6 +606,8 @@ extern "C" int nib_tc_gemm_bf16(const void* d_A, const void* d_B, float* d_C, in
   kp.cblocks = plan.cblocks;
   kp.S = 1;
   kp.n_tiles = ceil_div(N, plan.block_n);
+  kp.tile_rows = TC_BLOCK_M;
+  kp.a_bytes = TC_BLOCK_M * TC_BLOCK_K * 2;
   kp.err_flag = g_err_flag;
   const int tiles = ceil_div(M, TC_BLOCK_M) * kp.n_tiles;
   return tc_dispatch(&plan, kp, tiles, (cudaStream_t)stream);

@@ -7,6 +7,7 @@ namespace nib {
 struct ConvParams {
   const void* in;       // NHWC activations (T)
   const void* w;        // KRSC weights (T)
+  const void* w_alt;    // stem only: bf16 [Cout][7][8][8] (filter row, 7 taps + 1 filler, 8 padded channels) or null
   const float* bias;    // [Cout] fp32 or null
   const void* res;      // residual NHWC (T) or null
   void* out;
@@ -48,6 +49,7 @@ bool tc_conv_supported(const ConvParams& p);
 // builds tensor maps for the given buffers (max_batch images); returns NIB_OK or error
 int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out);
 void tc_conv_plan_destroy(TcConvPlan* plan);
+int tc_conv_plan_block_n(const TcConvPlan* plan);
 // launch for a batch with M = N*P*Q valid rows (p.M)
 int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st);
 

@@ -377,6 +377,7 @@ static int g_stats_cap = 0;
 
 int mask_synth_impl(const nib_mask_args* a, cudaStream_t st) {
   NIB_REQUIRE(a != nullptr, "nib_mask_synth: null args");
+  if (a->N == 0) return NIB_OK;  // an empty batch is legal (and its tensors have null data pointers)
   NIB_REQUIRE(a->d_img && a->d_labels && a->d_sel && a->d_out, "nib_mask_synth: null device pointer");
   NIB_REQUIRE(a->N >= 0 && a->C >= 1 && a->C <= kMaxC, "nib_mask_synth: C=%d unsupported (1..%d)", a->C, kMaxC);
   NIB_REQUIRE(a->H > 0 && a->W > 0 && a->S > 0, "nib_mask_synth: bad geometry H=%d W=%d S=%d", a->H, a->W, a->S);

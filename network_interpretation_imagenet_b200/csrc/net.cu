@@ -23,6 +23,7 @@ struct NetOp {
   int kind;  // 0 conv, 1 pool, 2 fc
   nib_conv_desc cd;
   void* d_w;          // conv: KRSC in net dtype; fc: fp32 [Cout][Cin]
+  void* d_w_alt;      // 7x7/2 stem in bf16 nets: [Cout][7][8][8] packing for the tcgen05 row-window path
   float* d_bias;
   float* d_pre_scale;
   float* d_pre_shift;
@@ -106,6 +107,7 @@ int nib_net_destroy(nib_net* net) {
     if (b.ptr) cudaFree(b.ptr);
   for (auto& o : net->ops) {
     if (o.d_w) cudaFree(o.d_w);
+    if (o.d_w_alt) cudaFree(o.d_w_alt);
     if (o.d_bias) cudaFree(o.d_bias);
     if (o.d_pre_scale) cudaFree(o.d_pre_scale);
     if (o.d_pre_shift) cudaFree(o.d_pre_shift);
@@ -174,6 +176,17 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
   } else {
     NIB_CUDA(cudaMalloc(&op.d_w, nel * 4 + 256));
     NIB_CUDA(cudaMemcpy(op.d_w, krsc.data(), nel * 4, cudaMemcpyHostToDevice));
+  }
+  if (net->bf16 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Cin <= 8 && bi.C == 8 && bi.pad == 3) {
+    std::vector<uint16_t> hb((size_t)d->Cout * 7 * 64, 0);
+    for (int co = 0; co < d->Cout; ++co)
+      for (int r = 0; r < 7; ++r)
+        for (int s = 0; s < 7; ++s)
+          for (int c = 0; c < d->Cin; ++c)
+            hb[(((size_t)co * 7 + r) * 8 + s) * 8 + c] =
+                f32_to_bf16_rn(h_weight[(((size_t)co * d->Cin + c) * 7 + r) * 7 + s]);
+    NIB_CUDA(cudaMalloc(&op.d_w_alt, hb.size() * 2 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w_alt, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
   }
   int rc = upload_floats(h_bias, d->Cout, &op.d_bias);
   if (rc != NIB_OK) return rc;
@@ -245,6 +258,7 @@ static void fill_conv_params(const nib_net* net, const NetOp& op, int N, ConvPar
   memset(p, 0, sizeof(*p));
   p->in = bi.ptr;
   p->w = op.d_w;
+  p->w_alt = op.d_w_alt;
   p->bias = op.d_bias;
   p->out = bo.ptr;
   p->pre_scale = op.d_pre_scale;
@@ -272,7 +286,10 @@ int nib_net_finalize(nib_net* net) {
       fill_conv_params(net, op, net->max_batch, &p);
       if (tc_conv_supported(p)) {
         int rc = tc_conv_plan_create(p, net->max_batch, &op.plan);
-        if (rc != NIB_OK) return rc;
+        if (rc != NIB_OK) {
+          if (op.d_w_alt == nullptr) return rc;
+          op.plan = nullptr;   // the stem's overlapping-window map is optional: the CUDA-core kernel covers it
+        }
       }
     }
   }
@@ -382,8 +399,8 @@ int nib_net_forward(nib_net* net, const void* d_x, int x_layout, int N, float* d
   return NIB_OK;
 }
 
-int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int cap, int* num_ops,
-                    void* stream) {
+int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int* h_geom, int cap,
+                    int* num_ops, void* stream) {
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(net && net->finalized && h_ms && h_kind && h_flops && num_ops, "nib_net_profile: bad arguments");
   NIB_REQUIRE(N > 0 && N <= net->max_batch, "nib_net_profile: bad N");
@@ -414,12 +431,26 @@ int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flo
       const NetBuffer& bo = net->bufs[op.cd.out_buf];
       h_kind[i] = (op.plan && net->use_tc) ? 1 : 0;
       h_flops[i] = 2.0 * N * bo.H * bo.W * (double)op.cd.R * op.cd.S * op.cd.Cin * op.cd.Cout;
+      if (h_geom) {
+        int* g = h_geom + 8 * i;
+        g[0] = bo.H; g[1] = bo.W; g[2] = op.cd.Cin; g[3] = op.cd.Cout; g[4] = op.cd.R; g[5] = op.cd.stride;
+        g[6] = op.cd.res_buf >= 0; g[7] = op.plan ? tc_conv_plan_block_n(op.plan) : 0;
+      }
     } else if (op.kind == 1) {
       h_kind[i] = 2;
       h_flops[i] = 0.0;
+      if (h_geom) {
+        const NetBuffer& bo = net->bufs[op.out_buf];
+        int* g = h_geom + 8 * i;
+        g[0] = bo.H; g[1] = bo.W; g[2] = op.C; g[3] = op.C; g[4] = op.k; g[5] = op.stride; g[6] = 0; g[7] = 0;
+      }
     } else {
       h_kind[i] = 3;
       h_flops[i] = 2.0 * N * (double)op.fc_cin * op.fc_cout;
+      if (h_geom) {
+        int* g = h_geom + 8 * i;
+        g[0] = 1; g[1] = 1; g[2] = op.fc_cin; g[3] = op.fc_cout; g[4] = 1; g[5] = 1; g[6] = 0; g[7] = 0;
+      }
     }
   }
   *num_ops = nops;

@@ -40,8 +40,14 @@ def gather_scores(local: torch.Tensor, N: int, group=None) -> torch.Tensor:
 
 
 class PerturbationEngine:
+    """refine_ties: relative top-2 margin (top1 - runner-up) / max|logit| below which a bf16-scored mask is
+    re-scored by an fp32 copy of the classifier.  bf16 logits agree with the reference's fp32 logits to <= 1e-2
+    relative, so a mask whose margin is inside ~3x that band could flip its arg-max; re-scoring exactly those keeps
+    top-1 identical to the reference on every mask at a cost proportional to the number of near-ties."""
+
     def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
-                 max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False):
+                 max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False,
+                 refine_ties: float | None = None):
         _lib.load()
         self.device = torch.device(device)
         self.target = int(target)
@@ -50,10 +56,22 @@ class PerturbationEngine:
         self.synth = MaskSynth(image, segments, S=S, device=device)
         self.classifier = model if isinstance(model, Classifier) else Classifier.from_torch(
             model, (self.synth.H, self.synth.W), precision=precision, max_batch=max_batch)
+        self.refine_ties = refine_ties if self.classifier.precision == "bf16" else None
+        self._model_src = None if isinstance(model, Classifier) else model
+        self._fp32 = None
+        self.refined = 0
+        if self.refine_ties is not None and self._model_src is None:
+            raise ValueError("refine_ties needs the torch module (to lower an fp32 copy), not a lowered Classifier")
         if use_graph:
             self.classifier.set_graph(True)
         self.rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def _fp32_classifier(self) -> Classifier:
+        if self._fp32 is None:
+            self._fp32 = Classifier.from_torch(self._model_src, (self.synth.H, self.synth.W), precision="fp32",
+                                               max_batch=min(self.classifier.max_batch, 64))
+        return self._fp32
 
     def score_local(self, sel_bits, out: torch.Tensor | None = None):
         """Scores for the given selections on this rank only.  Returns [n, 2] fp32: (target_prob, top1)."""
@@ -67,6 +85,14 @@ class PerturbationEngine:
         s = score(logits, self.target)
         out[:n, 0] = s["target_prob"]
         out[:n, 1] = s["top1"].to(torch.float32)   # class ids < 2^24 are exact in fp32
+        if self.refine_ties is not None:
+            idx = torch.nonzero(s["margin"] < self.refine_ties).flatten()   # one host sync per call
+            if idx.numel() > 0:
+                self.refined += int(idx.numel())
+                lg = self._fp32_classifier().forward_masked(self.synth, d_sel[idx], self.mode)
+                s2 = score(lg, self.target)
+                out[idx, 0] = s2["target_prob"]
+                out[idx, 1] = s2["top1"].to(torch.float32)
         return out
 
     def score_masks(self, sel_bits) -> dict:

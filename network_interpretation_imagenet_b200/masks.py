@@ -177,6 +177,8 @@ class MaskSynth:
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
             raise ValueError("out has the wrong shape/dtype")
         pm = torch.empty((N, self.H, self.W), dtype=torch.uint8, device=self.device) if return_pixel_masks else None
+        if N == 0:
+            return (out, pm) if return_pixel_masks else out
         odt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[dtype]
         a = self.mask_args(d_sel, mode, out, odt, lay, cs, pad, pm)
         _lib.check(self.lib.nib_mask_synth(C.byref(a), _lib.stream_handle()), "nib_mask_synth")

@@ -12,7 +12,8 @@ from . import _lib
 
 
 def score(logits: torch.Tensor, target: int, out=None):
-    """logits [N,K] fp32 cuda.  Returns dict(top1 int32[N], target_prob f32[N], max_prob f32[N], correct u8[N]).
+    """logits [N,K] fp32 cuda.  Returns dict(top1 int32[N], target_prob f32[N], max_prob f32[N], correct u8[N],
+    margin f32[N] = (top-1 logit - runner-up) / max|logit|, the bf16 tie detector).
     `out` may hold preallocated tensors under the same keys (e.g. slices of an all-gather buffer)."""
     lib = _lib.load()
     if not logits.is_cuda or logits.dtype != torch.float32 or not logits.is_contiguous():
@@ -24,7 +25,8 @@ def score(logits: torch.Tensor, target: int, out=None):
     out.setdefault("target_prob", torch.empty(N, dtype=torch.float32, device=dev))
     out.setdefault("max_prob", torch.empty(N, dtype=torch.float32, device=dev))
     out.setdefault("correct", torch.empty(N, dtype=torch.uint8, device=dev))
+    out.setdefault("margin", torch.empty(N, dtype=torch.float32, device=dev))
     _lib.check(lib.nib_score(logits.data_ptr(), N, K, int(target), out["top1"].data_ptr(),
                              out["target_prob"].data_ptr(), out["max_prob"].data_ptr(), out["correct"].data_ptr(),
-                             _lib.stream_handle()), "nib_score")
+                             out["margin"].data_ptr(), _lib.stream_handle()), "nib_score")
     return out

@@ -130,7 +130,11 @@ def _check_net(nib, model, x, precision, tol, max_batch=None):
     got = net.forward(torch.as_tensor(x).cuda()).cpu().numpy()
     err = rel_err(got, want)
     assert err <= tol, f"{precision}: rel err {err:.3e} > {tol}"
-    assert np.array_equal(got.argmax(1), want.argmax(1)), "top-1 differs"
+    # top-1 must agree wherever the reference's own top-2 margin is outside the logit tolerance band; inside it
+    # the engine's tie policy (PerturbationEngine.refine_ties, tested in test_gpu_engine.py) re-scores in fp32.
+    srt = np.sort(want, 1)
+    decided = (srt[:, -1] - srt[:, -2]) > 2 * tol * np.abs(want).max()
+    assert np.array_equal(got.argmax(1)[decided], want.argmax(1)[decided]), "top-1 differs outside the tie band"
     return net, got, want
 
 

@@ -74,14 +74,29 @@ def test_imagenet_config_end_to_end_bf16(nib):
     sels = nib.draw_selections("subset_keep", 50, 24, seed=1)
     target = int(ocls.forward_logits(model, x[None]).argmax(1)[0])
     (top1, tprob, _, _), logits = _oracle_loop(model, x, seg, sels, "keep", target)
-    eng = nib.PerturbationEngine(model, x, seg, target, mode=nib.KEEP_MUL, precision="bf16", max_batch=16, S=50)
+    eng = nib.PerturbationEngine(model, x, seg, target, mode=nib.KEEP_MUL, precision="bf16", max_batch=16, S=50,
+                                 refine_ties=0.03)
     bits = nib.selection_bits(sels, 50)
     got_logits = eng.classifier.forward_masked(eng.synth, bits, nib.KEEP_MUL).cpu().numpy()
     err = np.abs(got_logits - logits).max() / np.abs(logits).max()
     assert err <= 1e-2, err
     out = eng.score_masks(bits)
-    assert np.array_equal(out["top1"].cpu().numpy(), top1)
+    assert np.array_equal(out["top1"].cpu().numpy(), top1)      # identical top-1 on every mask (ties re-scored in fp32)
     np.testing.assert_allclose(out["target_prob"].cpu().numpy(), tprob, rtol=0.1, atol=1e-4)
+
+
+def test_densenet121_tie_refinement_gives_identical_top1(nib):
+    """A seeded random-init DenseNet-121 has near-tied logits (top-2 margin ~1e-2 of max|logit|): pure bf16 flips
+    some arg-maxes inside the 1e-2 logit tolerance; with refine_ties those masks are re-scored in fp32."""
+    x = synthetic.synthetic_image("imagenet")
+    seg = synthetic.voronoi_labels(224, 224, 50)
+    model = ocls.build_imagenet_model("densenet121")
+    sels = nib.draw_selections("subset_keep", 50, 16, seed=4)
+    (top1, tprob, _, _), logits = _oracle_loop(model, x, seg, sels, "keep", 0)
+    eng = nib.PerturbationEngine(model, x, seg, 0, mode=nib.KEEP_MUL, precision="bf16", max_batch=16, S=50,
+                                 refine_ties=0.05)
+    out = eng.score_masks(nib.selection_bits(sels, 50))
+    assert np.array_equal(out["top1"].cpu().numpy(), top1), (eng.refined, out["top1"].cpu().numpy(), top1)
 
 
 def test_two_rank_sharding_matches_single_gpu(nib):

@@ -72,7 +72,7 @@ def test_compute_fails_loudly_without_a_gpu(nib):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = nib._lib.load()
-    rc = lib.nib_score(None, 1, 10, 0, None, None, None, None, None)
+    rc = lib.nib_score(None, 1, 10, 0, None, None, None, None, None, None)
     assert rc == -3  # NIB_ENODEVICE: no CPU fallback
     assert b"no CPU fallback" in lib.nib_last_error() or b"fallback" in lib.nib_last_error()
     with pytest.raises(Exception):
