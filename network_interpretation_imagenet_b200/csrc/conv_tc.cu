@@ -51,6 +51,7 @@ struct TcKernelParams {
   int P, Q, stride, pad;
   int in_coff;
   int n_tiles;      // ceil(Cout / BLOCK_N)
+  int m_tiles;      // ceil(M / tile_rows)
   unsigned int* err_flag;
 };
 
@@ -345,6 +346,285 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// =====================================================================================================
+// v2: persistent kernel.  One CTA per SM loops over output tiles (n-tile fastest so the CTAs that share an
+// A tile run together and hit L2).  Differences from v1 that matter for the memory-heavy layers (1x1
+// expansions with residual, K = 64..256, where the epilogue — not the MMA — is the critical path):
+//   * accumulators are double-buffered in TMEM (2 x BLOCK_N columns): the MMA issuer starts tile i+1 while
+//     the epilogue warps drain tile i;
+//   * the residual tile is prefetched by the TMA producer into (double-buffered) swizzled smem while the
+//     main loop runs, instead of 64-byte strided global loads per lane;
+//   * the output goes registers -> swizzled smem box (128 rows x 64 channels) -> one TMA store per box:
+//     full 128 B lines instead of 32 sectors per store request (profiles/r01_ncu_conv_tc_v1_layer3.csv).
+template <int BLOCK_N, int STAGES, bool HAS_RES>
+struct Tc2Smem {
+  static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NBOX = BLOCK_N / 64;
+  static constexpr int BOX_BYTES = TC_BLOCK_M * 128;
+  static constexpr int RES_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int RES_BYTES = HAS_RES ? 2 * NBOX * BOX_BYTES : 0;
+  static constexpr int OUT_OFFSET = RES_OFFSET + RES_BYTES;
+  static constexpr int OUT_BYTES = 2 * BOX_BYTES;
+  static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 8;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int BLOCK_N, int STAGES, bool HAS_RES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                const TcKernelParams p) {
+  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + SM::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  auto res_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
+  auto res_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto res_box = [&](int buf, int b) { return smem_base + SM::RES_OFFSET + (uint32_t)(buf * SM::NBOX + b) * SM::BOX_BYTES; };
+  auto out_box = [&](int buf) { return smem_base + SM::OUT_OFFSET + (uint32_t)buf * SM::BOX_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  constexpr bool has_res = HAS_RES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
+    if (has_res) prefetch_tmap(&tmRes);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);
+      mbar_init(res_full_bar(b), 1);
+      mbar_init(res_empty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int m0 = m_tile * p.tile_rows;
+        const int n0 = n_tile * BLOCK_N;
+        int w0 = 0, h0 = 0, img = 0;
+        if (p.im2col == 1) {
+          const int pq = p.P * p.Q;
+          img = m0 / pq;
+          const int rem = m0 - img * pq;
+          const int pp = rem / p.Q, qq = rem - pp * p.Q;
+          w0 = qq * p.stride - p.pad;
+          h0 = pp * p.stride - p.pad;
+        } else if (p.im2col == 2) {
+          img = m_tile / p.P;
+          h0 = (m_tile - img * p.P) * p.stride;
+        }
+        if (has_res) {
+          const int rb = it & 1;
+          mbar_wait(res_empty_bar(rb), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 4);
+          mbar_arrive_expect_tx(res_full_bar(rb), (uint32_t)(SM::NBOX * SM::BOX_BYTES));
+#pragma unroll
+          for (int b = 0; b < SM::NBOX; ++b)
+            tma_load_2d(res_box(rb, b), &tmRes, res_full_bar(rb), p.res_coff + n0 + 64 * b, m0);
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+          const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + SM::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + SM::B_BYTES));
+          const int tap = kb / p.cblocks;
+          const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
+          if (p.im2col == 1) {
+            const int r = tap / p.S, s = tap - r * p.S;
+            tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+          } else if (p.im2col == 2) {
+            tma_load_4d(a_dst, &tmA, full_bar(stage), 0, 0, h0 + kb, img);
+          } else {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), c0, m0);
+          }
+          tma_load_2d(b_dst, &tmB, full_bar(stage), kb * TC_BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 2);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + SM::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(a_addr);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(ab));
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t row_off = (uint32_t)lrow * 128u;
+    const uint32_t sw = (uint32_t)(lrow & 7);
+    const bool leader = (warp == 2 && lane == 0);
+    int it = 0;
+    uint32_t nstore = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int m0 = m_tile * p.tile_rows;
+      const int n0 = n_tile * BLOCK_N;
+      const int ab = it & 1;
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      mbar_wait(tmem_full_bar(ab), ph, p.err_flag, 3);
+      tc_fence_after();
+      if (has_res) mbar_wait(res_full_bar(ab), ph, p.err_flag, 6);
+#pragma unroll 1
+      for (int b = 0; b < SM::NBOX; ++b) {
+        const int ob = (int)(nstore & 1u);
+        ++nstore;
+        if (leader) bulk_wait_read<1>();   // the store that last used staging buffer `ob` has finished reading it
+        epi_bar_sync();
+        const uint32_t obase = out_box(ob) + row_off;
+        const uint32_t rbase = res_box(ab, b) + row_off;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BLOCK_N + b * 64 + half * 32), v);
+          tmem_ld_wait();
+          if (b == SM::NBOX - 1 && half == 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const int col0 = n0 + b * 64 + half * 32;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+            }
+          }
+          if (has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 raw = lds_v4(rbase + ((((uint32_t)(half * 4 + c)) ^ sw) << 4));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 r2 = __bfloat1622float2(h2[t]);
+                f[c * 8 + 2 * t] += r2.x;
+                f[c * 8 + 2 * t + 1] += r2.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 o;
+            __nv_bfloat162 h;
+            h = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+            sts_v4(obase + ((((uint32_t)(half * 4 + c)) ^ sw) << 4), o);
+          }
+        }
+        if (has_res && b == SM::NBOX - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(res_empty_bar(ab));
+        }
+        fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (leader) {
+          tma_store_2d(&tmOut, out_box(ob), p.out_coff + n0 + b * 64, m0);
+          bulk_commit();
+        }
+      }
+    }
+    if (leader) bulk_wait_read<0>();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -371,7 +651,8 @@ static int load_driver_fns() {
 }
 
 struct TcConvPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  int v2;
   int block_n, stages;
   int im2col;
   int tile_rows;
@@ -424,15 +705,43 @@ bool tc_conv_supported(const ConvParams& p) {
   return true;
 }
 
-static int pick_block_n(int Cout) {
+static int pick_block_n(int Cout, bool has_res = true, int ksize = 1) {
   const char* e = getenv("NIB_TC_BLOCK_N");
   if (e) {
     int v = atoi(e);
     if ((v == 32 || v == 64 || v == 128 || v == 256) && Cout % v == 0) return v;
   }
+  // tuning knobs for the sweep: block-N of residual-free 3x3 / 1x1 layers
+  const char* e3 = getenv(ksize > 1 ? "NIB_TC_BLOCK_N_3X3" : "NIB_TC_BLOCK_N_1X1");
+  if (e3 && !has_res) {
+    int v = atoi(e3);
+    if ((v == 64 || v == 128 || v == 256) && Cout % v == 0) return v;
+  }
+  if (!has_res && Cout % 256 == 0) return 256;   // 128x256 tiles: 85 FLOP per byte of smem fill (L2 -> SM is the limiter)
   if (Cout % 128 == 0) return 128;
   if (Cout % 64 == 0) return 64;
   return 32;
+}
+
+// v2 (persistent, TMA-store epilogue) needs 64-column output boxes: BLOCK_N in {64,128}, Cout % BLOCK_N == 0.
+static int finish_plan(TcConvPlan* plan, const ConvParams& p, int max_batch) {
+  plan->v2 = 0;
+  const char* e = getenv("NIB_TC_V1");
+  if (e && atoi(e) != 0) return NIB_OK;
+  const bool bn_ok = plan->block_n == 64 || plan->block_n == 128 || (plan->block_n == 256 && p.res == nullptr);
+  if (!bn_ok || p.Cout % plan->block_n != 0) return NIB_OK;
+  const uint64_t rows = (uint64_t)max_batch * p.P * p.Q;
+  int rc = encode_2d_bf16(&plan->tmOut, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
+                          (uint32_t)plan->tile_rows);
+  if (rc != NIB_OK) return rc;
+  if (p.res != nullptr) {
+    rc = encode_2d_bf16(&plan->tmRes, p.res, (uint64_t)p.res_cstride, rows, (uint64_t)p.res_cstride * 2, 64, TC_BLOCK_M);
+    if (rc != NIB_OK) return rc;
+  } else {
+    plan->tmRes = plan->tmOut;
+  }
+  plan->v2 = 1;
+  return NIB_OK;
 }
 
 int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
@@ -445,7 +754,7 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
   TcConvPlan* plan = new TcConvPlan();
   memset(plan, 0, sizeof(*plan));
   plan->err_flag = g_err_flag;
-  plan->block_n = pick_block_n(p.Cout);
+  plan->block_n = pick_block_n(p.Cout, p.res != nullptr, p.R);
   plan->tile_rows = TC_BLOCK_M;
   if (tc_conv_is_stem(p)) {
     plan->im2col = 2;
@@ -467,6 +776,8 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
       delete plan;
       return NIB_ECUDA;
     }
+    rc = finish_plan(plan, p, max_batch);
+    if (rc != NIB_OK) { delete plan; return rc; }
     *out = plan;
     return NIB_OK;
   }
@@ -506,6 +817,8 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
     const uint64_t bytes = (uint64_t)max_batch * p.Hin * p.Win * p.in_cstride * 2;
     if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&plan->tmA)[1] &= ~(1ull << 21);
   }
+  rc = finish_plan(plan, p, max_batch);
+  if (rc != NIB_OK) { delete plan; return rc; }
   *out = plan;
   return NIB_OK;
 }
@@ -527,7 +840,32 @@ static int launch_tc(const TcConvPlan* plan, const TcKernelParams& kp, int tiles
   return NIB_OK;
 }
 
+template <int BLOCK_N, int STAGES, bool HAS_RES>
+static int launch_tc2(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
+  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES>;
+  static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NIB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES><<<grid, TC_THREADS, SM::TOTAL, st>>>(plan->tmA, plan->tmB, plan->tmOut,
+                                                                                  plan->tmRes, kp);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
 static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
+  if (plan->v2 && !kp.out_f32) {
+    // stage depth is what hides the L2 -> smem latency (Little's law: ~1.5 us x per-SM fill rate); the residual
+    // double buffer costs 2 x BLOCK_N/64 x 16 KB, so layers without a residual get the deeper ring.
+    const bool res = kp.res != nullptr;
+    if (plan->block_n == 64) return res ? launch_tc2<64, 5, true>(plan, kp, tiles, st) : launch_tc2<64, 7, false>(plan, kp, tiles, st);
+    if (plan->block_n == 128) return res ? launch_tc2<128, 3, true>(plan, kp, tiles, st) : launch_tc2<128, 5, false>(plan, kp, tiles, st);
+    if (plan->block_n == 256 && !res) return launch_tc2<256, 4, false>(plan, kp, tiles, st);
+  }
   switch (plan->block_n) {
     case 32:  return launch_tc<32, 4>(plan, kp, tiles, st);
     case 64:  return launch_tc<64, 4>(plan, kp, tiles, st);
@@ -565,7 +903,8 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.err_flag = plan->err_flag;
   kp.tile_rows = plan->tile_rows;
   kp.a_bytes = plan->tile_rows * TC_BLOCK_K * 2;
-  const int tiles = ceil_div(p.M, plan->tile_rows) * kp.n_tiles;
+  kp.m_tiles = ceil_div(p.M, plan->tile_rows);
+  const int tiles = kp.m_tiles * kp.n_tiles;
   return tc_dispatch(plan, kp, tiles, st);
 }
 
@@ -608,6 +947,7 @@ extern "C" int nib_tc_gemm_bf16(const void* d_A, const void* d_B, float* d_C, in
   kp.n_tiles = ceil_div(N, plan.block_n);
   kp.tile_rows = TC_BLOCK_M;
   kp.a_bytes = TC_BLOCK_M * TC_BLOCK_K * 2;
+  kp.m_tiles = ceil_div(M, TC_BLOCK_M);
   kp.err_flag = g_err_flag;
   const int tiles = ceil_div(M, TC_BLOCK_M) * kp.n_tiles;
   return tc_dispatch(&plan, kp, tiles, (cudaStream_t)stream);
