@@ -286,30 +286,53 @@ int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st) {
 }
 
 // ---- fully connected (fp32 weights, fp32 math; features in the net dtype) ---------------------
+// logits[n][k] = sum_c feat[n][c] * W[k][c] + b[k]: 16 samples x 64 classes per block (1 x 4 outputs per thread),
+// 32-wide K chunks staged in smem.  fp32 weights and math in both precisions (top-1 is decided here).
 template <typename T>
 __global__ void __launch_bounds__(256)
 fc_kernel(const T* __restrict__ feat, int feat_stride, const float* __restrict__ w, const float* __restrict__ b,
           int N, int Cin, int Cout, float* __restrict__ logits) {
-  // one warp per (n, k) output
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= (long long)N * Cout) return;
-  const int n = (int)(warp / Cout), k = (int)(warp % Cout);
-  const T* f = feat + (size_t)n * feat_stride;
-  const float* wr = w + (size_t)k * Cin;
-  float acc = 0.f;
-  for (int c = lane; c < Cin; c += 32) acc = fmaf(Elem<T>::ld(f + c), wr[c], acc);
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) logits[(size_t)n * Cout + k] = acc + (b ? b[k] : 0.f);
+  __shared__ float Fs[32][17];
+  __shared__ float Ws[32][65];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * 16, k0 = blockIdx.x * 64;
+  const int tn = tid >> 4, tk = tid & 15;   // sample tn, classes tk*4..+3
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < Cin; c0 += 32) {
+    for (int e = tid; e < 16 * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      Fs[c][r] = (n0 + r < N && c0 + c < Cin) ? Elem<T>::ld(feat + (size_t)(n0 + r) * feat_stride + c0 + c) : 0.f;
+    }
+    for (int e = tid; e < 64 * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      Ws[c][r] = (k0 + r < Cout && c0 + c < Cin) ? w[(size_t)(k0 + r) * Cin + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float f0 = Fs[c][tn];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(f0, Ws[c][tk * 4 + j], acc[j]);
+    }
+    __syncthreads();
+  }
+  const int n = n0 + tn;
+  if (n < N) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + j;
+      if (k < Cout) logits[(size_t)n * Cout + k] = acc[j] + (b ? b[k] : 0.f);
+    }
+  }
 }
 
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
               int Cout, float* logits, cudaStream_t st) {
-  unsigned blocks = (unsigned)ceil_div_ll((long long)N * Cout * 32, 256);
+  dim3 grid(ceil_div(Cout, 64), ceil_div(N, 16));
   if (bf16)
-    fc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)feat, feat_stride, w, b, N, Cin, Cout, logits);
+    fc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)feat, feat_stride, w, b, N, Cin, Cout, logits);
   else
-    fc_kernel<float><<<blocks, 256, 0, st>>>((const float*)feat, feat_stride, w, b, N, Cin, Cout, logits);
+    fc_kernel<float><<<grid, 256, 0, st>>>((const float*)feat, feat_stride, w, b, N, Cin, Cout, logits);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }

@@ -52,6 +52,7 @@ struct TcKernelParams {
   int in_coff;
   int n_tiles;      // ceil(Cout / BLOCK_N)
   int m_tiles;      // ceil(M / tile_rows)
+  int pf_dist;      // v2: L2-prefetch the operands of the tile this many iterations ahead (0 = off)
   unsigned int* err_flag;
 };
 
@@ -107,6 +108,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a future tile's operands: with one CTA per SM the smem ring holds < 1 tile of a K=256 layer, so a
+// DRAM-latency load (~3 us measured under load) throttles the ring to ring_bytes / latency.  Prefetching tiles that
+// are `pf_dist` iterations ahead into L2 turns those into L2-hit loads without spending shared memory.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* tm, int c, int w, int h, int n, uint16_t off_w,
+                                                       uint16_t off_h) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -357,19 +374,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //     main loop runs, instead of 64-byte strided global loads per lane;
 //   * the output goes registers -> swizzled smem box (128 rows x 64 channels) -> one TMA store per box:
 //     full 128 B lines instead of 32 sectors per store request (profiles/r01_ncu_conv_tc_v1_layer3.csv).
-template <int BLOCK_N, int STAGES, bool HAS_RES>
+static constexpr int TC2_EPI_WGS = 2;                         // epilogue warpgroups (one per TMEM accumulator buffer)
+static constexpr int TC2_THREADS = 64 + 128 * TC2_EPI_WGS;    // producer warp + MMA warp + epilogue warps
+static constexpr int TC2_BRES_KBLOCKS = 9;                    // resident-weights mode: up to 9 k-blocks (3x3 x 64 ch)
+
+// BRES: the whole weight matrix of the layer (Cout == BLOCK_N, <= 9 k-blocks) is loaded once per CTA and stays in
+// smem for every tile; the ring then carries A tiles only.  For the 64-channel layers (stem, 56x56 3x3) the
+// per-tile weight re-fetch was the dominant L2 -> SM traffic.
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES>
 struct Tc2Smem {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + (BRES ? 0 : B_BYTES);
   static constexpr int NBOX = BLOCK_N / 64;
   static constexpr int BOX_BYTES = TC_BLOCK_M * 128;
-  static constexpr int RES_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BRES_BYTES = BRES ? TC2_BRES_KBLOCKS * B_BYTES : 0;
+  static constexpr int RES_OFFSET = BRES_OFFSET + BRES_BYTES;
   static constexpr int RES_BYTES = HAS_RES ? 2 * NBOX * BOX_BYTES : 0;
   static constexpr int OUT_OFFSET = RES_OFFSET + RES_BYTES;
-  static constexpr int OUT_BYTES = 2 * BOX_BYTES;
+  static constexpr int OUT_BYTES = TC2_EPI_WGS * BOX_BYTES;   // one store-staging box per epilogue warpgroup
   static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 8;
+  static constexpr int NUM_BARS = 2 * STAGES + 9;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
@@ -385,7 +411,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -395,12 +421,12 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TcKernelParams p) {
-  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES>;
+  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + SM::BAR_OFFSET;
@@ -410,6 +436,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   auto res_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
   auto res_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
+  const uint32_t bres_full_bar = bar_base + 8u * (2 * STAGES + 8);
   const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   auto res_box = [&](int buf, int b) { return smem_base + SM::RES_OFFSET + (uint32_t)(buf * SM::NBOX + b) * SM::BOX_BYTES; };
@@ -436,6 +463,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(res_full_bar(b), 1);
       mbar_init(res_empty_bar(b), 4);
     }
+    mbar_init(bres_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -453,11 +481,47 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (BRES) {   // the layer's whole weight matrix, once
+        mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(p.num_k_blocks * SM::B_BYTES));
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          tma_load_2d(smem_base + SM::BRES_OFFSET + kb * SM::B_BYTES, &tmB, bres_full_bar, kb * TC_BLOCK_K, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int m0 = m_tile * p.tile_rows;
         const int n0 = n_tile * BLOCK_N;
+        if (p.pf_dist > 0) {
+          const int ft = tile + p.pf_dist * (int)gridDim.x;
+          if (ft < total_tiles) {
+            const int fn = ft % p.n_tiles, fm = ft / p.n_tiles;
+            const int fm0 = fm * p.tile_rows;
+            if (has_res) {
+#pragma unroll
+              for (int b = 0; b < SM::NBOX; ++b) tma_prefetch_2d(&tmRes, p.res_coff + fn * BLOCK_N + 64 * b, fm0);
+            }
+            // the A tile is shared by the n_tiles CTAs working on the same rows: one of them prefetches it
+            if (fn == 0 || p.n_tiles > (int)gridDim.x) {
+              if (p.im2col == 1) {
+                const int pq = p.P * p.Q;
+                const int fi = fm0 / pq, rem = fm0 - fi * pq;
+                const int pp = rem / p.Q, qq = rem - pp * p.Q;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                  const int tap = kb / p.cblocks;
+                  const int r = tap / p.S, sx = tap - r * p.S;
+                  tma_prefetch_im2col_4d(&tmA, (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff, qq * p.stride - p.pad,
+                                         pp * p.stride - p.pad, fi, (uint16_t)sx, (uint16_t)r);
+                }
+              } else if (p.im2col == 2) {
+                const int fi = fm / p.P;
+                const int fh = (fm - fi * p.P) * p.stride;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_prefetch_4d(&tmA, 0, 0, fh + kb, fi);
+              } else {
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_prefetch_2d(&tmA, kb * TC_BLOCK_K + p.in_coff, fm0);
+              }
+            }
+          }
+        }
         int w0 = 0, h0 = 0, img = 0;
         if (p.im2col == 1) {
           const int pq = p.P * p.Q;
@@ -482,7 +546,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
           const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
           const uint32_t b_dst = a_dst + SM::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + SM::B_BYTES));
+          mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + (BRES ? 0 : SM::B_BYTES)));
           const int tap = kb / p.cblocks;
           const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
           if (p.im2col == 1) {
@@ -493,7 +557,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             tma_load_2d(a_dst, &tmA, full_bar(stage), c0, m0);
           }
-          tma_load_2d(b_dst, &tmB, full_bar(stage), kb * TC_BLOCK_K, n0);
+          if (!BRES) tma_load_2d(b_dst, &tmB, full_bar(stage), kb * TC_BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -505,6 +569,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (BRES) mbar_wait(bres_full_bar, 0, p.err_flag, 7);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int ab = it & 1;
         mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5);
@@ -514,7 +579,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(full_bar(stage), phase, p.err_flag, 2);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + SM::A_BYTES;
+          const uint32_t b_addr = BRES ? smem_base + SM::BRES_OFFSET + kb * SM::B_BYTES : a_addr + SM::A_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(a_addr);
           const uint64_t bdesc = make_smem_desc_sw128(b_addr);
 #pragma unroll
@@ -527,15 +592,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ===== epilogue warps 2..5 =====
+    // ===== epilogue: warpgroup wg (warps 2+4wg .. 5+4wg) drains the tiles whose accumulator is TMEM buffer wg =====
+    const int wg = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;
     const uint32_t row_off = (uint32_t)lrow * 128u;
     const uint32_t sw = (uint32_t)(lrow & 7);
-    const bool leader = (warp == 2 && lane == 0);
-    int it = 0;
-    uint32_t nstore = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const bool leader = (warp == 2 + 4 * wg && lane == 0);
+    for (int tile = blockIdx.x + wg * (int)gridDim.x, it = wg; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int m0 = m_tile * p.tile_rows;
@@ -547,11 +611,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (has_res) mbar_wait(res_full_bar(ab), ph, p.err_flag, 6);
 #pragma unroll 1
       for (int b = 0; b < SM::NBOX; ++b) {
-        const int ob = (int)(nstore & 1u);
-        ++nstore;
-        if (leader) bulk_wait_read<1>();   // the store that last used staging buffer `ob` has finished reading it
-        epi_bar_sync();
-        const uint32_t obase = out_box(ob) + row_off;
+        if (leader) bulk_wait_read<0>();   // this warpgroup's previous store has finished reading its staging box
+        epi_bar_sync(wg);
+        const uint32_t obase = out_box(wg) + row_off;
         const uint32_t rbase = res_box(ab, b) + row_off;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -608,9 +670,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive(res_empty_bar(ab));
         }
         fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        epi_bar_sync();
+        epi_bar_sync(wg);
         if (leader) {
-          tma_store_2d(&tmOut, out_box(ob), p.out_coff + n0 + b * 64, m0);
+          tma_store_2d(&tmOut, out_box(wg), p.out_coff + n0 + b * 64, m0);
           bulk_commit();
         }
       }
@@ -840,19 +902,19 @@ static int launch_tc(const TcConvPlan* plan, const TcKernelParams& kp, int tiles
   return NIB_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES>
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
 static int launch_tc2(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
-  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES>;
+  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
   static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static bool attr_set = false;
   if (!attr_set) {
-    NIB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES>,
+    NIB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES, BRES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES><<<grid, TC_THREADS, SM::TOTAL, st>>>(plan->tmA, plan->tmB, plan->tmOut,
-                                                                                  plan->tmRes, kp);
+  conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES, BRES><<<grid, TC2_THREADS, SM::TOTAL, st>>>(plan->tmA, plan->tmB, plan->tmOut,
+                                                                                         plan->tmRes, kp);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }
@@ -862,6 +924,9 @@ static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int til
     // stage depth is what hides the L2 -> smem latency (Little's law: ~1.5 us x per-SM fill rate); the residual
     // double buffer costs 2 x BLOCK_N/64 x 16 KB, so layers without a residual get the deeper ring.
     const bool res = kp.res != nullptr;
+    static const bool no_bres = getenv("NIB_TC_NO_BRES") != nullptr;
+    if (plan->block_n == 64 && !res && kp.n_tiles == 1 && kp.num_k_blocks <= TC2_BRES_KBLOCKS && !no_bres)
+      return launch_tc2<64, 6, false, true>(plan, kp, tiles, st);   // resident weights: stem, 56x56 64-channel layers
     if (plan->block_n == 64) return res ? launch_tc2<64, 5, true>(plan, kp, tiles, st) : launch_tc2<64, 7, false>(plan, kp, tiles, st);
     if (plan->block_n == 128) return res ? launch_tc2<128, 3, true>(plan, kp, tiles, st) : launch_tc2<128, 5, false>(plan, kp, tiles, st);
     if (plan->block_n == 256 && !res) return launch_tc2<256, 4, false>(plan, kp, tiles, st);
@@ -904,6 +969,11 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.tile_rows = plan->tile_rows;
   kp.a_bytes = plan->tile_rows * TC_BLOCK_K * 2;
   kp.m_tiles = ceil_div(p.M, plan->tile_rows);
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("NIB_TC_PF"); pf = e ? atoi(e) : 2; }
+    kp.pf_dist = pf;
+  }
   const int tiles = kp.m_tiles * kp.n_tiles;
   return tc_dispatch(plan, kp, tiles, st);
 }
