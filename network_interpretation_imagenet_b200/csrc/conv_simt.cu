@@ -286,49 +286,69 @@ int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st) {
 }
 
 // ---- fully connected (fp32 weights, fp32 math; features in the net dtype) ---------------------
-// logits[n][k] = sum_c feat[n][c] * W[k][c] + b[k]: 16 samples x 64 classes per block (1 x 4 outputs per thread),
-// 32-wide K chunks staged in smem.  fp32 weights and math in both precisions (top-1 is decided here).
+// logits[n][k] = sum_c feat[n][c] * W[k][c] + b[k].  Register-tiled SGEMM: 32 samples x 64 classes per block,
+// 2 x 4 outputs per thread, 32-wide K chunks staged (transposed) in smem; global loads are issued for chunk i+1
+// before the FMAs of chunk i.  fp32 weights and fp32 math in both precisions: top-1 is decided here.
+static constexpr int FC_BM = 32, FC_BN = 64, FC_BK = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 fc_kernel(const T* __restrict__ feat, int feat_stride, const float* __restrict__ w, const float* __restrict__ b,
           int N, int Cin, int Cout, float* __restrict__ logits) {
-  __shared__ float Fs[32][17];
-  __shared__ float Ws[32][65];
+  __shared__ float Fs[FC_BK][FC_BM + 2];
+  __shared__ __align__(16) float Ws[FC_BK][FC_BN + 4];
   const int tid = threadIdx.x;
-  const int n0 = blockIdx.y * 16, k0 = blockIdx.x * 64;
-  const int tn = tid >> 4, tk = tid & 15;   // sample tn, classes tk*4..+3
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c0 = 0; c0 < Cin; c0 += 32) {
-    for (int e = tid; e < 16 * 32; e += 256) {
-      const int r = e >> 5, c = e & 31;
-      Fs[c][r] = (n0 + r < N && c0 + c < Cin) ? Elem<T>::ld(feat + (size_t)(n0 + r) * feat_stride + c0 + c) : 0.f;
+  const int n0 = blockIdx.y * FC_BM, k0 = blockIdx.x * FC_BN;
+  const int ty = tid >> 4, tx = tid & 15;   // samples 2ty, 2ty+1; classes 4tx..4tx+3
+  // loader roles: feature element (row fr, k fc*4..+3); weight elements (row wr and wr+32, k wc*4..+3)
+  const int fr = tid >> 3, fc = tid & 7;
+  const int wr = tid >> 3, wc = tid & 7;
+  float acc[2][4] = {};
+  float fv[4], wv0[4], wv1[4];
+  auto load_chunk = [&](int c0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + fc * 4 + j;
+      fv[j] = (n0 + fr < N && c < Cin) ? Elem<T>::ld(feat + (size_t)(n0 + fr) * feat_stride + c) : 0.f;
+      wv0[j] = (k0 + wr < Cout && c < Cin) ? __ldg(w + (size_t)(k0 + wr) * Cin + c) : 0.f;
+      wv1[j] = (k0 + wr + 32 < Cout && c < Cin) ? __ldg(w + (size_t)(k0 + wr + 32) * Cin + c) : 0.f;
     }
-    for (int e = tid; e < 64 * 32; e += 256) {
-      const int r = e >> 5, c = e & 31;
-      Ws[c][r] = (k0 + r < Cout && c0 + c < Cin) ? w[(size_t)(k0 + r) * Cin + c0 + c] : 0.f;
+  };
+  load_chunk(0);
+  for (int c0 = 0; c0 < Cin; c0 += FC_BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      Fs[fc * 4 + j][fr] = fv[j];
+      Ws[wc * 4 + j][wr] = wv0[j];
+      Ws[wc * 4 + j][wr + 32] = wv1[j];
     }
     __syncthreads();
+    if (c0 + FC_BK < Cin) load_chunk(c0 + FC_BK);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const float f0 = Fs[c][tn];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(f0, Ws[c][tk * 4 + j], acc[j]);
+    for (int c = 0; c < FC_BK; ++c) {
+      const float a0 = Fs[c][2 * ty], a1 = Fs[c][2 * ty + 1];
+      const float4 bv = *reinterpret_cast<const float4*>(&Ws[c][4 * tx]);
+      acc[0][0] = fmaf(a0, bv.x, acc[0][0]); acc[0][1] = fmaf(a0, bv.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, bv.z, acc[0][2]); acc[0][3] = fmaf(a0, bv.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, bv.x, acc[1][0]); acc[1][1] = fmaf(a1, bv.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, bv.z, acc[1][2]); acc[1][3] = fmaf(a1, bv.w, acc[1][3]);
     }
     __syncthreads();
   }
-  const int n = n0 + tn;
-  if (n < N) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = n0 + 2 * ty + i;
+    if (n >= N) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = k0 + tk * 4 + j;
-      if (k < Cout) logits[(size_t)n * Cout + k] = acc[j] + (b ? b[k] : 0.f);
+      const int k = k0 + 4 * tx + j;
+      if (k < Cout) logits[(size_t)n * Cout + k] = acc[i][j] + (b ? b[k] : 0.f);
     }
   }
 }
 
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
               int Cout, float* logits, cudaStream_t st) {
-  dim3 grid(ceil_div(Cout, 64), ceil_div(N, 16));
+  dim3 grid(ceil_div(Cout, FC_BN), ceil_div(N, FC_BM));
   if (bf16)
     fc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)feat, feat_stride, w, b, N, Cin, Cout, logits);
   else

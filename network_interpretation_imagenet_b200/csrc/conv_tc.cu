@@ -54,6 +54,7 @@ struct TcKernelParams {
   int m_tiles;      // ceil(M / tile_rows)
   int pf_dist;      // v2: L2-prefetch the operands of the tile this many iterations ahead (0 = off)
   unsigned int* err_flag;
+  unsigned long long* dbg;   // NIB_TC_DBG=1: per-CTA role timers (cycles), 16 slots per CTA; null in production
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -687,6 +688,468 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// =====================================================================================================
+// v3: CTA-pair kernel (tcgen05 cta_group::2).  Two CTAs of a (2,1,1) cluster sit on the two SMs of a TPC and
+// compute one 256 x BLOCK_N output tile together: each CTA loads its own 128 activation rows and HALF of the
+// weight tile (BLOCK_N/2 rows); the leader CTA issues one M=256 MMA per K step that reads A and B from both
+// CTAs' shared memory and writes rows 0..127 of the accumulator into its own TMEM and rows 128..255 into the
+// peer's.  Per output element this halves the weight traffic L2 -> SM, which is what bounded v2
+// (profiles/README.md: 694 MB of smem fill per 3x3 256->256 launch = 11.7 TB/s, the measured L2 ceiling).
+//   * smem ring per CTA: STAGES x (16 KB A + BLOCK_N/2 x 128 B of B); both CTAs' TMA loads complete on the
+//     LEADER's full barrier, one tcgen05.commit.multicast frees the slot in both CTAs;
+//   * TMEM: 2 accumulator buffers of BLOCK_N columns per CTA (all 512 columns at BLOCK_N = 256);
+//   * epilogue: 8 warps (2 warpgroups, each owns half of the tile's columns) in each CTA drain their own
+//     TMEM lanes; the residual box is TMA-loaded into the SAME smem box the result is staged in (add in
+//     place), so a 128 x 256 tile with residual still leaves room for a 5-deep ring;
+//   * the tile order keeps the CTA pairs that share activation rows adjacent in time (n fastest).
+static constexpr int TC3_THREADS = 64 + 256;
+
+template <int BLOCK_N, int STAGES, bool HAS_RES>
+struct Tc3Smem {
+  static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
+  static constexpr int BH_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;   // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+  static constexpr int NBOX = BLOCK_N / 64;                          // 64-channel output boxes per tile
+  static constexpr bool SPLIT_COLS = NBOX >= 2;                      // warpgroup g drains columns [g*BLOCK_N/2, ...) of every
+                                                                     // tile; BLOCK_N = 64: warpgroup g drains the tiles in TMEM buffer g
+  static constexpr int CW = SPLIT_COLS ? BLOCK_N / 2 : 64;           // columns one warpgroup drains per tile
+  static constexpr int UNITS = CW / 64;                              // 64-channel boxes per warpgroup per tile
+  static constexpr int BOX_BYTES = TC_BLOCK_M * 128;
+  static constexpr int RSETS = HAS_RES ? (BLOCK_N == 256 ? 1 : 2) : 1;
+  static constexpr int NBUF = HAS_RES ? RSETS * NBOX : 2;            // residual/output boxes, or 8 x 4 KB per-warp staging
+  static constexpr int BOX_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = BOX_OFFSET + NBUF * BOX_BYTES;   // [warpgroup][2][CW] floats: the tile's folded-BN bias
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * 2 * CW * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF;
+  static constexpr int EMPTY_ARRIVALS = SPLIT_COLS ? 16 : 8;         // epilogue warps (both CTAs) that drain one accumulator
+  // dynamic smem is the only shared allocation of the kernel, so it starts 1024-aligned in the CTA window; the kernel
+  // checks that (the 128B swizzle needs it) instead of spending 1 KB of slack on it
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// pair loads: data lands in this CTA's smem, the transaction bytes are counted on the leader CTA's barrier
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c,
+                                                    int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+        "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+        "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+        "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
+// packed epilogue math: two fp32 lanes per instruction (FADD2), one convert per bf16 pair, ReLU on the packed pair
+__device__ __forceinline__ uint64_t pack_f32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t a) {   // {lo, hi} fp32 -> bf16x2 (lo in the low half), RN
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(a));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {   // NaN-propagating, like torch.relu
+  uint32_t r;
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BLOCK_N>
+__host__ __device__ constexpr uint32_t make_idesc_bf16_pair() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES, bool HAS_RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutTail,
+                const __grid_constant__ CUtensorMap tmRes, const TcKernelParams p) {
+  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) {
+    if (threadIdx.x == 0 && p.err_flag) atomicExch(p.err_flag, 9u);
+    __trap();
+  }
+  const uint32_t bar_base = smem_base + SM::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                         // used in the leader CTA
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); }; // used in the leader CTA
+  auto res_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
+  auto box_free_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + SM::NBUF + b); };
+  const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto box_addr = [&](int buf) { return smem_base + SM::BOX_OFFSET + (uint32_t)buf * SM::BOX_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int total_tiles = m_pairs * p.n_tiles;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  // role timers (debug builds of a launch only: p.dbg != null)
+  const bool dbg_on = p.dbg != nullptr;
+  long long t_acc[4] = {0, 0, 0, 0};
+  long long t_loop0 = 0;
+  if (dbg_on && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[(size_t)blockIdx.x * 16 + 12] = gt;
+    p.dbg[(size_t)blockIdx.x * 16 + 14] = (unsigned long long)clock64();
+  }
+#define TC3_TIMED(slot, stmt)                                      \
+  do {                                                             \
+    if (dbg_on) { const long long _t = clock64(); stmt; t_acc[slot] += clock64() - _t; } \
+    else { stmt; }                                                 \
+  } while (0)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
+    if (HAS_RES) prefetch_tmap(&tmRes);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), SM::EMPTY_ARRIVALS);   // the epilogue warps of both CTAs that drain one accumulator
+    }
+    for (int b = 0; b < SM::NBUF; ++b) {
+      mbar_init(res_full_bar(b), 1);
+      mbar_init(box_free_bar(b), 4);   // the four warps that store a box hand it back
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
+      // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
+      // busy epilogue never stalls the operand ring
+      int pend_b = SM::NBOX, pend_set = 0, pend_m0 = 0, pend_n0 = 0;
+      uint32_t pend_par = 0;
+      auto issue_pending = [&](bool block) {
+        while (pend_b < SM::NBOX) {
+          const int buf = pend_set * SM::NBOX + pend_b;
+          if (block) TC3_TIMED(1, mbar_wait(box_free_bar(buf), pend_par ^ 1u, p.err_flag, 4));
+          else if (!mbar_try_wait(box_free_bar(buf), pend_par ^ 1u)) return;
+          mbar_arrive_expect_tx(res_full_bar(buf), (uint32_t)SM::BOX_BYTES);
+          tma_load_2d(box_addr(buf), &tmRes, res_full_bar(buf), p.res_coff + pend_n0 + 64 * pend_b, pend_m0);
+          ++pend_b;
+        }
+      };
+      if (dbg_on) t_loop0 = clock64();
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+        const int m0 = m_tile * p.tile_rows;
+        const int n0 = n_tile * BLOCK_N;
+        int w0 = 0, h0 = 0, img = 0;
+        if (p.im2col == 1) {
+          const int pq = p.P * p.Q;
+          img = m0 / pq;
+          const int rem = m0 - img * pq;
+          const int pp = rem / p.Q, qq = rem - pp * p.Q;
+          w0 = qq * p.stride - p.pad;
+          h0 = pp * p.stride - p.pad;
+        } else if (p.im2col == 2) {
+          img = m_tile / p.P;
+          h0 = (m_tile - img * p.P) * p.stride;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          if (HAS_RES) issue_pending(false);
+          TC3_TIMED(0, mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1));
+          const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + SM::A_BYTES;
+          const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * (p.a_bytes + SM::BH_BYTES)));
+          const int tap = kb / p.cblocks;
+          const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
+          if (p.im2col == 1) {
+            const int r = tap / p.S, s = tap - r * p.S;
+            tma2_load_im2col_4d(a_dst, &tmA, lbar, c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+          } else if (p.im2col == 2) {
+            tma2_load_4d(a_dst, &tmA, lbar, 0, 0, h0 + kb, img);
+          } else {
+            tma2_load_2d(a_dst, &tmA, lbar, c0, m0);
+          }
+          tma2_load_2d(b_dst, &tmB, lbar, kb * TC_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (HAS_RES) {
+          issue_pending(true);   // the tile before this one: its boxes were freed at least one whole tile ago
+          pend_b = 0;
+          pend_set = it % SM::RSETS;
+          pend_par = (uint32_t)((it / SM::RSETS) & 1);
+          pend_m0 = m0;
+          pend_n0 = n0;
+        }
+      }
+      if (HAS_RES) issue_pending(true);
+      if (dbg_on) {
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+        d[0] = (unsigned long long)t_acc[0]; d[1] = (unsigned long long)t_acc[1];
+        d[8] = (unsigned long long)(clock64() - t_loop0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = make_idesc_bf16_pair<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      if (dbg_on) t_loop0 = clock64();
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+        const int ab = it & 1;
+        TC3_TIMED(1, mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(a_addr);
+          const uint64_t bdesc = make_smem_desc_sw128(a_addr + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+            umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma2_commit_both(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma2_commit_both(tmem_full_bar(ab));
+      }
+      if (dbg_on) {
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+        d[2] = (unsigned long long)t_acc[0]; d[3] = (unsigned long long)t_acc[1];
+        d[9] = (unsigned long long)(clock64() - t_loop0);
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps per CTA, every warp an independent pipeline =====
+    // A warp drains its 32 TMEM lanes (= 32 output rows) of the columns its warpgroup owns, 64 channels at a time:
+    // tcgen05.ld -> bias / residual / ReLU (packed) -> swizzled 4 KB smem slab -> its own 32-row TMA store.  No
+    // warp waits for another one except for the once-per-tile bias hand-over inside its warpgroup.
+    const int ew = warp - 2;
+    const int g = ew >> 2;
+    const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+    const int lrow = quarter * 32 + lane;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int wt = (int)threadIdx.x - 64 - g * 128;        // 0..127 inside the warpgroup
+    const uint32_t lead_empty0 = mapa_shared(tmem_empty_bar(0), 0);
+    const uint32_t lead_empty1 = mapa_shared(tmem_empty_bar(1), 0);
+    const bool has_bias = p.bias != nullptr;
+    const uint32_t relu_floor = p.relu ? 0u : 0xFF80FF80u; // max.bf16x2 against (0,0) or (-inf,-inf)
+    const int colbase = SM::SPLIT_COLS ? g * SM::CW : 0;   // first tile column of this warpgroup
+    const uint32_t bias_wg = smem_base + SM::BIAS_OFFSET + (uint32_t)(g * 2 * SM::CW * 4);
+    const int rows_here = p.tile_rows - quarter * 32;      // valid rows of this warp's slab (stem tiles have 112 rows)
+    const int step = SM::SPLIT_COLS ? npairs : 2 * npairs;
+    int it = SM::SPLIT_COLS ? 0 : g;
+    int lt = 0;
+    int tile = SM::SPLIT_COLS ? pair : pair + g * npairs;
+    // With ~225 KB of the SM carved out as shared memory there is no L1 to speak of: the tile's bias slice is fetched
+    // one tile ahead into a register, parked in smem and read back as broadcast LDS.128.
+    float bias_pre = 0.f;
+    if (has_bias && wt < SM::CW && tile < total_tiles) bias_pre = __ldg(p.bias + (tile % p.n_tiles) * BLOCK_N + colbase + wt);
+    if (dbg_on) t_loop0 = clock64();
+    for (; tile < total_tiles; tile += step, it += (SM::SPLIT_COLS ? 1 : 2), ++lt) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+      const int m0 = m_tile * p.tile_rows;
+      const int n0 = n_tile * BLOCK_N;
+      const int ab = it & 1;
+      TC3_TIMED(0, mbar_wait(tmem_full_bar(ab), (uint32_t)((it >> 1) & 1), p.err_flag, 3));
+      tc_fence_after();
+      const uint32_t bias_s = bias_wg + (uint32_t)((lt & 1) * SM::CW * 4);
+      if (has_bias) {
+        if (wt < SM::CW) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * wt), "f"(bias_pre) : "memory");
+        TC3_TIMED(3, named_bar_sync(1 + g, 128));
+        const int nt = tile + step;
+        if (wt < SM::CW && nt < total_tiles) bias_pre = __ldg(p.bias + (nt % p.n_tiles) * BLOCK_N + colbase + wt);
+      }
+      const int set = it % SM::RSETS;
+      const uint32_t rpar = (uint32_t)((it / SM::RSETS) & 1);
+#pragma unroll 1
+      for (int u = 0; u < SM::UNITS; ++u) {
+        const int b = SM::SPLIT_COLS ? g * SM::UNITS + u : 0;                   // output box (64 channels) of the tile
+        const int buf = set * SM::NBOX + b;                                    // residual/output box (HAS_RES)
+        const uint32_t slab = HAS_RES ? box_addr(buf) + (uint32_t)(quarter * 4096)
+                                      : smem_base + SM::BOX_OFFSET + (uint32_t)(ew * 4096);
+        const uint32_t obase = slab + (uint32_t)lane * 128u;
+        if (HAS_RES) TC3_TIMED(1, mbar_wait(res_full_bar(buf), rpar, p.err_flag, 6));
+        uint32_t v[64];
+        __syncwarp();
+        tmem_ld_32x32b_x64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BLOCK_N + b * 64), v);
+        tmem_ld_wait();
+        if (u == SM::UNITS - 1) {    // this warp has read its whole share of the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(ab ? lead_empty1 : lead_empty0);
+        }
+        uint32_t o[32];
+        const uint32_t bsrc = bias_s + (uint32_t)(u * 64 * 4);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {          // 8 chunks of 8 channels (16 B of bf16)
+          uint64_t a0 = pack_f32x2(v[c * 8 + 0], v[c * 8 + 1]), a1 = pack_f32x2(v[c * 8 + 2], v[c * 8 + 3]);
+          uint64_t a2 = pack_f32x2(v[c * 8 + 4], v[c * 8 + 5]), a3 = pack_f32x2(v[c * 8 + 6], v[c * 8 + 7]);
+          if (has_bias) {
+            const uint4 b0 = lds_v4(bsrc + (uint32_t)(c * 32)), b1 = lds_v4(bsrc + (uint32_t)(c * 32 + 16));
+            a0 = add_f32x2(a0, pack_f32x2(b0.x, b0.y)); a1 = add_f32x2(a1, pack_f32x2(b0.z, b0.w));
+            a2 = add_f32x2(a2, pack_f32x2(b1.x, b1.y)); a3 = add_f32x2(a3, pack_f32x2(b1.z, b1.w));
+          }
+          if (HAS_RES) {
+            const uint4 r = lds_v4(obase + ((((uint32_t)c) ^ sw) << 4));   // 8 bf16 residual values of this row
+            a0 = add_f32x2(a0, pack_f32x2(r.x << 16, r.x & 0xFFFF0000u)); a1 = add_f32x2(a1, pack_f32x2(r.y << 16, r.y & 0xFFFF0000u));
+            a2 = add_f32x2(a2, pack_f32x2(r.z << 16, r.z & 0xFFFF0000u)); a3 = add_f32x2(a3, pack_f32x2(r.w << 16, r.w & 0xFFFF0000u));
+          }
+          o[c * 4 + 0] = max_bf16x2(cvt_bf16x2(a0), relu_floor); o[c * 4 + 1] = max_bf16x2(cvt_bf16x2(a1), relu_floor);
+          o[c * 4 + 2] = max_bf16x2(cvt_bf16x2(a2), relu_floor); o[c * 4 + 3] = max_bf16x2(cvt_bf16x2(a3), relu_floor);
+        }
+        if (!HAS_RES) {              // private slab: the previous store of this warp must have read it
+          if (lane == 0) TC3_TIMED(2, bulk_wait_read<0>());
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts_v4(obase + ((((uint32_t)c) ^ sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
+        fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          if (rows_here >= 32) tma_store_2d(&tmOut, slab, p.out_coff + n0 + b * 64, m0 + quarter * 32);
+          else if (rows_here > 0) tma_store_2d(&tmOutTail, slab, p.out_coff + n0 + b * 64, m0 + quarter * 32);
+          bulk_commit();
+          if (HAS_RES) {
+            // hand boxes back to the producer as soon as the store engine has read them
+            if (u > 0) {
+              TC3_TIMED(2, bulk_wait_read<1>());
+              mbar_arrive(box_free_bar(buf - 1));
+            }
+            if (u == SM::UNITS - 1) {
+              TC3_TIMED(2, bulk_wait_read<0>());
+              mbar_arrive(box_free_bar(buf));
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    if (dbg_on && warp == 2 && lane == 0) {
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+      d[4] = (unsigned long long)t_acc[0]; d[5] = (unsigned long long)t_acc[1];
+      d[6] = (unsigned long long)t_acc[2]; d[7] = (unsigned long long)t_acc[3];
+      d[10] = (unsigned long long)(clock64() - t_loop0);
+      d[11] = (unsigned long long)lt;
+    }
+    tc_fence_before();
+  }
+#undef TC3_TIMED
+  __syncthreads();
+  cluster_sync_all();   // no CTA of the pair retires (or frees TMEM) while the other may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+  if (dbg_on && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[(size_t)blockIdx.x * 16 + 13] = gt;
+    p.dbg[(size_t)blockIdx.x * 16 + 15] = (unsigned long long)clock64();
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -714,7 +1177,10 @@ static int load_driver_fns() {
 
 struct TcConvPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
+  CUtensorMap tmBh;   // v3: weight map with a BLOCK_N/2-row box (each CTA of the pair loads half of the tile)
+  CUtensorMap tmOut32, tmOutTail;   // v3: per-warp 32-row output boxes (+ the short last box of a 112-row stem tile)
   int v2;
+  int v3;
   int block_n, stages;
   int im2col;
   int tile_rows;
@@ -767,6 +1233,7 @@ bool tc_conv_supported(const ConvParams& p) {
   return true;
 }
 
+static int tc_version();
 static int pick_block_n(int Cout, bool has_res = true, int ksize = 1) {
   const char* e = getenv("NIB_TC_BLOCK_N");
   if (e) {
@@ -779,18 +1246,31 @@ static int pick_block_n(int Cout, bool has_res = true, int ksize = 1) {
     int v = atoi(e3);
     if ((v == 64 || v == 128 || v == 256) && Cout % v == 0) return v;
   }
-  if (!has_res && Cout % 256 == 0) return 256;   // 128x256 tiles: 85 FLOP per byte of smem fill (L2 -> SM is the limiter)
+  if ((!has_res || tc_version() >= 3) && Cout % 256 == 0) return 256;   // 128x256 tiles per CTA: L2 -> SM fill is the limiter
   if (Cout % 128 == 0) return 128;
   if (Cout % 64 == 0) return 64;
   return 32;
 }
 
 // v2 (persistent, TMA-store epilogue) needs 64-column output boxes: BLOCK_N in {64,128}, Cout % BLOCK_N == 0.
-static int finish_plan(TcConvPlan* plan, const ConvParams& p, int max_batch) {
+static int tc_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NIB_TC_VER");
+    v = e ? atoi(e) : 3;
+    if (v < 1 || v > 3) v = 3;
+    const char* e1 = getenv("NIB_TC_V1");
+    if (e1 && atoi(e1) != 0) v = 1;
+  }
+  return v;
+}
+
+static int finish_plan(TcConvPlan* plan, const ConvParams& p, int max_batch, const void* w_ptr, int K) {
   plan->v2 = 0;
-  const char* e = getenv("NIB_TC_V1");
-  if (e && atoi(e) != 0) return NIB_OK;
-  const bool bn_ok = plan->block_n == 64 || plan->block_n == 128 || (plan->block_n == 256 && p.res == nullptr);
+  plan->v3 = 0;
+  if (tc_version() == 1) return NIB_OK;
+  const bool bn_ok = plan->block_n == 64 || plan->block_n == 128 ||
+                     (plan->block_n == 256 && (p.res == nullptr || tc_version() >= 3));
   if (!bn_ok || p.Cout % plan->block_n != 0) return NIB_OK;
   const uint64_t rows = (uint64_t)max_batch * p.P * p.Q;
   int rc = encode_2d_bf16(&plan->tmOut, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
@@ -803,6 +1283,18 @@ static int finish_plan(TcConvPlan* plan, const ConvParams& p, int max_batch) {
     plan->tmRes = plan->tmOut;
   }
   plan->v2 = 1;
+  if (tc_version() >= 3) {
+    rc = encode_2d_bf16(&plan->tmBh, w_ptr, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, TC_BLOCK_K,
+                        (uint32_t)(plan->block_n / 2));
+    if (rc != NIB_OK) return rc;
+    rc = encode_2d_bf16(&plan->tmOut32, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64, 32);
+    if (rc != NIB_OK) return rc;
+    const int tail = plan->tile_rows % 32;
+    rc = encode_2d_bf16(&plan->tmOutTail, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
+                        (uint32_t)(tail ? tail : 32));
+    if (rc != NIB_OK) return rc;
+    plan->v3 = 1;
+  }
   return NIB_OK;
 }
 
@@ -838,7 +1330,7 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
       delete plan;
       return NIB_ECUDA;
     }
-    rc = finish_plan(plan, p, max_batch);
+    rc = finish_plan(plan, p, max_batch, p.w_alt, 7 * 64);
     if (rc != NIB_OK) { delete plan; return rc; }
     *out = plan;
     return NIB_OK;
@@ -879,7 +1371,7 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
     const uint64_t bytes = (uint64_t)max_batch * p.Hin * p.Win * p.in_cstride * 2;
     if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&plan->tmA)[1] &= ~(1ull << 21);
   }
-  rc = finish_plan(plan, p, max_batch);
+  rc = finish_plan(plan, p, max_batch, p.w, K);
   if (rc != NIB_OK) { delete plan; return rc; }
   *out = plan;
   return NIB_OK;
@@ -919,7 +1411,33 @@ static int launch_tc2(const TcConvPlan* plan, const TcKernelParams& kp, int tile
   return NIB_OK;
 }
 
+template <int BLOCK_N, int STAGES, bool HAS_RES>
+static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStream_t st) {
+  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES>;
+  static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NIB_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  const int pair_tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+  conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES><<<2 * pairs, TC3_THREADS, SM::TOTAL, st>>>(
+      plan->tmA, plan->tmBh, plan->tmOut32, plan->tmOutTail, plan->tmRes, kp);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
 static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
+  if (plan->v3 && !kp.out_f32) {
+    // CTA-pair kernel; stage counts fill the 227 KB of each SM (ring + output/residual boxes)
+    const bool res = kp.res != nullptr;
+    if (plan->block_n == 256) return res ? launch_tc3<256, 5, true>(plan, kp, st) : launch_tc3<256, 6, false>(plan, kp, st);
+    if (plan->block_n == 128) return res ? launch_tc3<128, 6, true>(plan, kp, st) : launch_tc3<128, 8, false>(plan, kp, st);
+    if (plan->block_n == 64) return res ? launch_tc3<64, 9, true>(plan, kp, st) : launch_tc3<64, 9, false>(plan, kp, st);
+  }
   if (plan->v2 && !kp.out_f32) {
     // stage depth is what hides the L2 -> smem latency (Little's law: ~1.5 us x per-SM fill rate); the residual
     // double buffer costs 2 x BLOCK_N/64 x 16 KB, so layers without a residual get the deeper ring.
@@ -939,6 +1457,59 @@ static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int til
   }
   set_error("tc_dispatch: bad block_n %d", plan->block_n);
   return NIB_EINVAL;
+}
+
+// NIB_TC_DBG=1: run the launch with the role timers on, synchronise and print where each warp role of the CTA-pair
+// kernel spent its time (average over CTAs, microseconds at the SM clock).  Diagnostic only.
+static int tc_launch_debug(const TcConvPlan* plan, TcKernelParams kp, const ConvParams& p, int tiles, cudaStream_t st) {
+  static unsigned long long* d_dbg = nullptr;
+  const int nslots = 160 * 16;
+  if (!d_dbg) NIB_CUDA(cudaMalloc(&d_dbg, nslots * sizeof(unsigned long long)));
+  NIB_CUDA(cudaMemsetAsync(d_dbg, 0, nslots * sizeof(unsigned long long), st));
+  kp.dbg = d_dbg;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  int rc = tc_dispatch(plan, kp, tiles, st);
+  cudaEventRecord(e1, st);
+  if (rc != NIB_OK) return rc;
+  NIB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  static unsigned long long h[160 * 16];
+  NIB_CUDA(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+  int clk_khz = 1965000;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  const double us = 1e3 / (double)clk_khz;   // cycles -> us
+  double a[16] = {0};
+  int nc = 0;
+  unsigned long long g0 = ~0ull, g1 = 0, g0max = 0, g1min = ~0ull;
+  double mhz = 0, loop_max = 0;
+  for (int c = 0; c < 148; ++c) {
+    if (h[c * 16 + 8] == 0) continue;
+    ++nc;
+    for (int j = 0; j < 12; ++j) a[j] += (double)h[c * 16 + j];
+    const unsigned long long e = h[c * 16 + 12], x = h[c * 16 + 13];
+    if (e < g0) g0 = e;
+    if (e > g0max) g0max = e;
+    if (x > g1) g1 = x;
+    if (x < g1min) g1min = x;
+    if (x > e) mhz += (double)(h[c * 16 + 15] - h[c * 16 + 14]) / (double)(x - e) * 1e3;
+    if ((double)h[c * 16 + 10] > loop_max) loop_max = (double)h[c * 16 + 10];
+  }
+  fprintf(stderr, "[tc3t] in-kernel span %.1f us (first entry -> last exit), entry skew %.1f us, exit skew %.1f us, SM clock %.0f MHz, "
+          "max epi loop %.1f us\n", (g1 - g0) / 1e3, (g0max - g0) / 1e3, (g1 - g1min) / 1e3, mhz / (nc ? nc : 1), loop_max * us);
+  if (nc == 0) nc = 1;
+  for (int j = 0; j < 16; ++j) a[j] = a[j] / nc * us;
+  // leader-only slots (MMA) are averaged over all CTAs: scale back
+  fprintf(stderr,
+          "[tc3] %dx%d %d->%d k%d s%d res%d bn%d M=%d tiles/cta=%.1f  %.1f us | prod: loop %.1f wait_empty %.1f wait_box %.1f"
+          " | mma(x2): loop %.1f wait_full %.1f wait_tmem %.1f | epi: loop %.1f wait_tmem_full %.1f wait_res %.1f"
+          " store_drain %.1f bar %.1f\n",
+          p.P, p.Q, p.Cin, p.Cout, p.R, p.stride, p.res != nullptr, plan->block_n, p.M, a[11], ms * 1e3, a[8], a[0], a[1],
+          2 * a[9], 2 * a[2], 2 * a[3], a[10], a[4], a[5], a[6], a[7]);
+  return NIB_OK;
 }
 
 int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st) {
@@ -971,10 +1542,12 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.m_tiles = ceil_div(p.M, plan->tile_rows);
   {
     static int pf = -1;
-    if (pf < 0) { const char* e = getenv("NIB_TC_PF"); pf = e ? atoi(e) : 2; }
+    if (pf < 0) { const char* e = getenv("NIB_TC_PF"); pf = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/README.md), off by default
     kp.pf_dist = pf;
   }
   const int tiles = kp.m_tiles * kp.n_tiles;
+  static const bool dbg = getenv("NIB_TC_DBG") != nullptr;
+  if (dbg && plan->v3) return tc_launch_debug(plan, kp, p, tiles, st);
   return tc_dispatch(plan, kp, tiles, st);
 }
 

@@ -1,0 +1,20 @@
+#!/bin/bash
+# first contact of the CTA-pair kernel (conv_tc3): per-geometry diagnostics, classifier tests, bench v3 vs v2
+mkdir -p gpurun_out
+timeout 1200 python tools/tc_diag.py > gpurun_out/tc_diag_v3.log 2>&1
+cp gpurun_out/tc_diag.txt gpurun_out/tc_diag_v3.txt
+grep "^conv" gpurun_out/tc_diag_v3.txt | cut -c1-220
+timeout 900 python -m pytest tests/test_gpu_classifier.py tests/test_gpu_engine.py -q -m gpu -p no:cacheprovider -x > gpurun_out/pytest_gpu_v3.log 2>&1
+echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_v3.log
+run() { name=$1; mb=$2; shift; shift; env "$@" timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gp --micro-batch $mb --masks-per-step $((mb*8)) --profile-json gpurun_out/profile_$name.json > gpurun_out/bench_$name.log 2>gpurun_out/bench_$name.err; echo -n "$name: "; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_$name.log").read().strip().splitlines()[-1]); r=d["roofline"]
+    print(round(d["value"]), "evals/s  e2e", round(d["e2e"]["value"]), " tc TF/s", round(r["achieved"],1), r["per_kind_ms"])
+except Exception as e: print("ERR", e, open("gpurun_out/bench_$name.err").read()[-600:])
+PY
+}
+run v3_mb256 256 NIB_TC_VER=3
+run v2_mb256 256 NIB_TC_VER=2
+run v3_mb288 288 NIB_TC_VER=3
+run v3_mb512 512 NIB_TC_VER=3

@@ -50,6 +50,10 @@ CONVS = [
     (64, 64, 1, 1, 0, 16, 16, False, False), (64, 64, 3, 1, 1, 16, 16, False, False), (64, 64, 3, 1, 1, 14, 14, False, False),
     (128, 128, 3, 2, 1, 28, 28, False, False), (256, 512, 1, 2, 0, 28, 28, False, False), (64, 256, 1, 1, 0, 14, 14, True, True),
     (128, 32, 3, 1, 1, 7, 7, False, False),
+    # CTA-pair kernel coverage: every (BLOCK_N, residual) instantiation, multi-tile K, odd tile counts
+    (64, 64, 1, 1, 0, 14, 14, True, True), (128, 128, 1, 1, 0, 28, 28, True, True), (256, 1024, 1, 1, 0, 14, 14, True, True),
+    (1024, 256, 1, 1, 0, 14, 14, True, False), (256, 256, 3, 1, 1, 14, 14, True, False), (512, 128, 1, 1, 0, 28, 28, True, False),
+    (128, 512, 1, 1, 0, 28, 28, True, True), (512, 2048, 1, 1, 0, 7, 7, True, True), (64, 256, 1, 1, 0, 56, 56, True, True),
 ]
 
 
