@@ -781,6 +781,15 @@ __device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const CUtensor
       "h"(off_h)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // true in exactly one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -910,83 +919,97 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // The producer and MMA roles run their loops with the whole warp converged and elect one lane only around the
+  // asynchronous instructions themselves: loop state stays in uniform registers, so each TMA / MMA issue is a handful of
+  // instructions (a role nested inside `if (lane == 0)` makes the compiler wrap every UTMALDG / UTCHMMA in an
+  // ELECT + R2UR.BROADCAST waterfall, ~100 cycles per issue, which was the actual ceiling of the 64-channel layers).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (both CTAs) =====
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
-      // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
-      // busy epilogue never stalls the operand ring
-      int pend_b = SM::NBOX, pend_set = 0, pend_m0 = 0, pend_n0 = 0;
-      uint32_t pend_par = 0;
-      auto issue_pending = [&](bool block) {
-        while (pend_b < SM::NBOX) {
-          const int buf = pend_set * SM::NBOX + pend_b;
-          if (block) TC3_TIMED(1, mbar_wait(box_free_bar(buf), pend_par ^ 1u, p.err_flag, 4));
-          else if (!mbar_try_wait(box_free_bar(buf), pend_par ^ 1u)) return;
+    // ===== TMA producer (both CTAs) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const uint32_t lbar0 = mapa_shared(full_bar(0), 0);   // leader CTA's full barriers
+    const uint32_t tx_bytes = (uint32_t)(2 * (p.a_bytes + SM::BH_BYTES));
+    const int b_row0 = (int)rank * (BLOCK_N / 2);
+    // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
+    // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
+    // busy epilogue never stalls the operand ring
+    int pend_b = SM::NBOX, pend_set = 0, pend_m0 = 0, pend_n0 = 0;
+    uint32_t pend_par = 0;
+    auto issue_pending = [&](bool block) {
+      while (pend_b < SM::NBOX) {
+        const int buf = pend_set * SM::NBOX + pend_b;
+        if (block) {
+          TC3_TIMED(1, mbar_wait(box_free_bar(buf), pend_par ^ 1u, p.err_flag, 4));
+        } else {
+          const int ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(box_free_bar(buf), pend_par ^ 1u), 0);
+          if (!ready) return;
+        }
+        if (elect_one()) {
           mbar_arrive_expect_tx(res_full_bar(buf), (uint32_t)SM::BOX_BYTES);
           tma_load_2d(box_addr(buf), &tmRes, res_full_bar(buf), p.res_coff + pend_n0 + 64 * pend_b, pend_m0);
-          ++pend_b;
         }
-      };
-      if (dbg_on) t_loop0 = clock64();
-      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
-        const int m0 = m_tile * p.tile_rows;
-        const int n0 = n_tile * BLOCK_N;
-        int w0 = 0, h0 = 0, img = 0;
-        if (p.im2col == 1) {
-          const int pq = p.P * p.Q;
-          img = m0 / pq;
-          const int rem = m0 - img * pq;
-          const int pp = rem / p.Q, qq = rem - pp * p.Q;
-          w0 = qq * p.stride - p.pad;
-          h0 = pp * p.stride - p.pad;
-        } else if (p.im2col == 2) {
-          img = m_tile / p.P;
-          h0 = (m_tile - img * p.P) * p.stride;
-        }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          if (HAS_RES) issue_pending(false);
-          TC3_TIMED(0, mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1));
+        __syncwarp();
+        ++pend_b;
+      }
+    };
+    if (dbg_on) t_loop0 = clock64();
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+      const int m0 = m_tile * p.tile_rows;
+      const int n0 = n_tile * BLOCK_N;
+      int w0 = 0, h0 = 0, img = 0;
+      if (p.im2col == 1) {
+        const int pq = p.P * p.Q;
+        img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int pp = rem / p.Q, qq = rem - pp * p.Q;
+        w0 = qq * p.stride - p.pad;
+        h0 = pp * p.stride - p.pad;
+      } else if (p.im2col == 2) {
+        img = m_tile / p.P;
+        h0 = (m_tile - img * p.P) * p.stride;
+      }
+      int cb = 0, tap_s = 0, tap_r = 0;   // k-block -> (filter row, filter column, 64-channel block), kept incrementally
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        if (HAS_RES) issue_pending(false);
+        TC3_TIMED(0, mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1));
+        if (elect_one()) {
           const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + SM::A_BYTES;
-          const uint32_t lbar = mapa_shared(full_bar(stage), 0);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * (p.a_bytes + SM::BH_BYTES)));
-          const int tap = kb / p.cblocks;
-          const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
+          const uint32_t lbar = lbar0 + 8u * stage;
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+          const int c0 = cb * TC_BLOCK_K + p.in_coff;
           if (p.im2col == 1) {
-            const int r = tap / p.S, s = tap - r * p.S;
-            tma2_load_im2col_4d(a_dst, &tmA, lbar, c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+            tma2_load_im2col_4d(a_dst, &tmA, lbar, c0, w0, h0, img, (uint16_t)tap_s, (uint16_t)tap_r);
           } else if (p.im2col == 2) {
             tma2_load_4d(a_dst, &tmA, lbar, 0, 0, h0 + kb, img);
           } else {
             tma2_load_2d(a_dst, &tmA, lbar, c0, m0);
           }
-          tma2_load_2d(b_dst, &tmB, lbar, kb * TC_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          tma2_load_2d(a_dst + SM::A_BYTES, &tmB, lbar, kb * TC_BLOCK_K, n0 + b_row0);
         }
-        if (HAS_RES) {
-          issue_pending(true);   // the tile before this one: its boxes were freed at least one whole tile ago
-          pend_b = 0;
-          pend_set = it % SM::RSETS;
-          pend_par = (uint32_t)((it / SM::RSETS) & 1);
-          pend_m0 = m0;
-          pend_n0 = n0;
-        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
       }
-      if (HAS_RES) issue_pending(true);
-      if (dbg_on) {
-        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
-        d[0] = (unsigned long long)t_acc[0]; d[1] = (unsigned long long)t_acc[1];
-        d[8] = (unsigned long long)(clock64() - t_loop0);
+      if (HAS_RES) {
+        issue_pending(true);   // the tile before this one: its boxes were freed at least one whole tile ago
+        pend_b = 0;
+        pend_set = it % SM::RSETS;
+        pend_par = (uint32_t)((it / SM::RSETS) & 1);
+        pend_m0 = m0;
+        pend_n0 = n0;
       }
     }
+    if (HAS_RES) issue_pending(true);
+    if (dbg_on && lane == 0) {
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+      d[0] = (unsigned long long)t_acc[0]; d[1] = (unsigned long long)t_acc[1];
+      d[8] = (unsigned long long)(clock64() - t_loop0);
+    }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ===== MMA issuer (leader CTA only) =====
       constexpr uint32_t idesc = make_idesc_bf16_pair<BLOCK_N>();
       int stage = 0;
@@ -1001,18 +1024,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(a_addr);
-          const uint64_t bdesc = make_smem_desc_sw128(a_addr + SM::A_BYTES);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc_sw128(a_addr);
+            const uint64_t bdesc = make_smem_desc_sw128(a_addr + SM::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-            umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma2_commit_both(empty_bar(stage));
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+              umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            umma2_commit_both(empty_bar(stage));
+            if (kb == p.num_k_blocks - 1) umma2_commit_both(tmem_full_bar(ab));
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma2_commit_both(tmem_full_bar(ab));
       }
-      if (dbg_on) {
+      if (dbg_on && lane == 0) {
         unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
         d[2] = (unsigned long long)t_acc[0]; d[3] = (unsigned long long)t_acc[1];
         d[9] = (unsigned long long)(clock64() - t_loop0);
@@ -1026,7 +1052,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 2;
     const int g = ew >> 2;
     const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
-    const int lrow = quarter * 32 + lane;
     const uint32_t sw = (uint32_t)(lane & 7);
     const int wt = (int)threadIdx.x - 64 - g * 128;        // 0..127 inside the warpgroup
     const uint32_t lead_empty0 = mapa_shared(tmem_empty_bar(0), 0);

@@ -11,8 +11,8 @@ try:
 except Exception as e: print("ERR", e, open("gpurun_out/bench_$name.err").read()[-600:])
 PY
 }
-run v3c_mb256 256 NIB_TC_VER=3
-run v3c_mb288 288 NIB_TC_VER=3
-run v3c_mb512 512 NIB_TC_VER=3
+run v3d_mb256 256 NIB_TC_VER=3
+run v3d_mb288 288 NIB_TC_VER=3
+run v3d_mb512 512 NIB_TC_VER=3
 NIB_TC_DBG=1 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gp --micro-batch 256 --masks-per-step 256 > gpurun_out/dbg_bench.log 2> gpurun_out/dbg_roles.txt
 grep "^\[tc3" gpurun_out/dbg_roles.txt | tail -208 > gpurun_out/dbg_roles_last.txt
