@@ -285,6 +285,44 @@ int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st) {
   return NIB_OK;
 }
 
+// ---- pre-activation pack (DenseNet BN-ReLU-conv on the tensor-core path) ------------------------
+// y[m][c] = relu(x[m][in_coff + c] * scale[c] + shift[c]) for c < Cin, 0 for Cin <= c < Cpad, written compactly as
+// [M][Cpad] bf16 so the tcgen05 conv can read it through TMA (models/densenet.py:16-21 applies norm1/relu1 per consumer
+// to the shared concat buffer, so it cannot be folded into the producer).  8 channels (16 B) per thread.
+__global__ void __launch_bounds__(256)
+bnrelu_pack_kernel(const __nv_bfloat16* __restrict__ x, int in_cstride, int in_coff, int Cin, int Cpad,
+                   const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                   long long M) {
+  const int groups = Cpad >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * groups) return;
+  const long long m = idx / groups;
+  const int c0 = (int)(idx - m * groups) << 3;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (c0 < Cin) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + (size_t)m * in_cstride + in_coff + c0);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+    const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float2 a = __bfloat1622float2(v[0]), b = __bfloat1622float2(v[1]), c = __bfloat1622float2(v[2]), d = __bfloat1622float2(v[3]);
+    __nv_bfloat162 r;
+    r = __floats2bfloat162_rn(fmaxf(fmaf(a.x, s0.x, h0.x), 0.f), fmaxf(fmaf(a.y, s0.y, h0.y), 0.f)); o.x = *reinterpret_cast<uint32_t*>(&r);
+    r = __floats2bfloat162_rn(fmaxf(fmaf(b.x, s0.z, h0.z), 0.f), fmaxf(fmaf(b.y, s0.w, h0.w), 0.f)); o.y = *reinterpret_cast<uint32_t*>(&r);
+    r = __floats2bfloat162_rn(fmaxf(fmaf(c.x, s1.x, h1.x), 0.f), fmaxf(fmaf(c.y, s1.y, h1.y), 0.f)); o.z = *reinterpret_cast<uint32_t*>(&r);
+    r = __floats2bfloat162_rn(fmaxf(fmaf(d.x, s1.z, h1.z), 0.f), fmaxf(fmaf(d.y, s1.w, h1.w), 0.f)); o.w = *reinterpret_cast<uint32_t*>(&r);
+  }
+  *reinterpret_cast<uint4*>(y + (size_t)m * Cpad + c0) = o;
+}
+
+int launch_bnrelu_pack(const void* x, int in_cstride, int in_coff, int Cin, int Cpad, const float* scale,
+                       const float* shift, void* y, long long M, cudaStream_t st) {
+  const long long total = M * (Cpad >> 3);
+  bnrelu_pack_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)x, in_cstride, in_coff, Cin, Cpad, scale, shift, (__nv_bfloat16*)y, M);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
 // ---- fully connected (fp32 weights, fp32 math; features in the net dtype) ---------------------
 // logits[n][k] = sum_c feat[n][c] * W[k][c] + b[k].  Register-tiled SGEMM: 32 samples x 64 classes per block,
 // 2 x 4 outputs per thread, 32-wide K chunks staged (transposed) in smem; global loads are issued for chunk i+1

@@ -918,6 +918,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();   // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, cluster
+  // handshake) ran while the previous layer's kernel was still draining; from here on we touch its output.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // The producer and MMA roles run their loops with the whole warp converged and elect one lane only around the
   // asynchronous instructions themselves: loop state stays in uniform registers, so each TMA / MMA issue is a handful of
@@ -1449,9 +1453,24 @@ static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStre
   const int pair_tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
   const int max_pairs = num_sms() / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
-  conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES><<<2 * pairs, TC3_THREADS, SM::TOTAL, st>>>(
-      plan->tmA, plan->tmBh, plan->tmOut32, plan->tmOutTail, plan->tmRes, kp);
-  NIB_LAUNCH_CHECK();
+  // launched with programmatic stream serialization: the CTAs become resident (and run their prologue) as the SMs of
+  // the previous kernel free up, then block in griddepcontrol.wait until that kernel has completed
+  static const bool pdl = getenv("NIB_TC_NO_PDL") == nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(TC3_THREADS);
+  cfg.dynamicSmemBytes = SM::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && cap == cudaStreamCaptureStatusNone && kp.dbg == nullptr) ? 1 : 0;
+  NIB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES>, plan->tmA, plan->tmBh, plan->tmOut32,
+                              plan->tmOutTail, plan->tmRes, kp));
   return NIB_OK;
 }
 

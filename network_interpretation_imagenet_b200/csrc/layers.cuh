@@ -35,6 +35,8 @@ int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st);
 int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st);
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
               int Cout, float* logits, cudaStream_t st);
+int launch_bnrelu_pack(const void* x, int in_cstride, int in_coff, int Cin, int Cpad, const float* scale,
+                       const float* shift, void* y, long long M, cudaStream_t st);
 int launch_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* out, int cs, int halo, bool bf16,
                         cudaStream_t st);
 int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int halo, bool bf16, float* out,

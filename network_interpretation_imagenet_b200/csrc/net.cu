@@ -27,6 +27,8 @@ struct NetOp {
   float* d_bias;
   float* d_pre_scale;
   float* d_pre_shift;
+  void* d_w_pack;     // pre-activation convs in bf16 nets: KRSC weights with Cin zero-padded to a multiple of 64
+  int pack_cin;       // that padded Cin (0: no packed tensor-core path for this op)
   TcConvPlan* plan;
   // pool
   int pool_kind, k, stride, pad, C, in_buf, in_coff, out_buf, out_coff;
@@ -40,6 +42,8 @@ struct nib_net {
   bool bf16;
   std::vector<NetBuffer> bufs;
   std::vector<NetOp> ops;
+  void* pack_scratch;        // [max_batch * H * W][pack_cin] bf16: relu(bn(x)) of the conv being run (largest such layer)
+  size_t pack_scratch_bytes;
   int input_buf;
   bool finalized;
   int num_classes;
@@ -91,6 +95,8 @@ int nib_net_create(int precision, int max_batch, nib_net** out) {
   n->bf16 = precision == NIB_PREC_BF16;
   n->max_batch = max_batch;
   n->input_buf = -1;
+  n->pack_scratch = nullptr;
+  n->pack_scratch_bytes = 0;
   n->finalized = false;
   n->num_classes = 0;
   n->use_tc = true;
@@ -105,8 +111,10 @@ int nib_net_destroy(nib_net* net) {
   for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
   for (auto& b : net->bufs)
     if (b.ptr) cudaFree(b.ptr);
+  if (net->pack_scratch) cudaFree(net->pack_scratch);
   for (auto& o : net->ops) {
     if (o.d_w) cudaFree(o.d_w);
+    if (o.d_w_pack) cudaFree(o.d_w_pack);
     if (o.d_w_alt) cudaFree(o.d_w_alt);
     if (o.d_bias) cudaFree(o.d_bias);
     if (o.d_pre_scale) cudaFree(o.d_pre_scale);
@@ -187,6 +195,21 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
                 f32_to_bf16_rn(h_weight[(((size_t)co * d->Cin + c) * 7 + r) * 7 + s]);
     NIB_CUDA(cudaMalloc(&op.d_w_alt, hb.size() * 2 + 256));
     NIB_CUDA(cudaMemcpy(op.d_w_alt, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  }
+  // BN-ReLU-conv (DenseNet) on the tensor-core path: the conv reads relu(bn(x)) from a packed scratch tensor whose
+  // channel count is rounded up to the 64-channel K block, so the weights get the same zero padding along Cin.
+  if (net->bf16 && (d->flags & NIB_CONV_PRE_BNRELU) && d->Cin % 8 == 0 && d->in_coff % 8 == 0 && bi.C % 8 == 0 &&
+      bi.pad == 0 && d->Cout % 32 == 0) {
+    const int cpad = (d->Cin + 63) / 64 * 64;
+    const size_t npad = (size_t)d->Cout * d->R * d->S * cpad;
+    std::vector<uint16_t> hb(npad, 0);
+    for (int co = 0; co < d->Cout; ++co)
+      for (int rs = 0; rs < d->R * d->S; ++rs)
+        for (int c = 0; c < d->Cin; ++c)
+          hb[((size_t)co * d->R * d->S + rs) * cpad + c] = f32_to_bf16_rn(krsc[((size_t)co * d->R * d->S + rs) * d->Cin + c]);
+    NIB_CUDA(cudaMalloc(&op.d_w_pack, npad * 2 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w_pack, hb.data(), npad * 2, cudaMemcpyHostToDevice));
+    op.pack_cin = cpad;
   }
   int rc = upload_floats(h_bias, d->Cout, &op.d_bias);
   if (rc != NIB_OK) return rc;
@@ -275,14 +298,44 @@ static void fill_conv_params(const nib_net* net, const NetOp& op, int N, ConvPar
   p->relu = (d.flags & NIB_CONV_RELU) ? 1 : 0;
 }
 
+// the same conv, reading the packed relu(bn(x)) scratch tensor instead of the raw channel slice
+static void fill_packed_conv_params(const nib_net* net, const NetOp& op, int N, ConvParams* p) {
+  fill_conv_params(net, op, N, p);
+  p->in = net->pack_scratch;
+  p->w = op.d_w_pack;
+  p->pre_scale = nullptr;
+  p->pre_shift = nullptr;
+  p->Cin = op.pack_cin;
+  p->in_cstride = op.pack_cin;
+  p->in_coff = 0;
+}
+
 int nib_net_finalize(nib_net* net) {
   NIB_REQUIRE(net && !net->finalized, "nib_net_finalize: bad handle/state");
   NIB_REQUIRE(net->input_buf >= 0, "nib_net_finalize: input buffer not set");
   NIB_REQUIRE(!net->ops.empty() && net->ops.back().kind == 2, "nib_net_finalize: the last op must be the fc layer");
   if (net->bf16) {
+    // one scratch tensor serves every packed pre-activation conv (ops run one at a time on the stream)
+    for (auto& op : net->ops) {
+      if (op.kind != 0 || op.pack_cin == 0) continue;
+      const NetBuffer& bi = net->bufs[op.cd.in_buf];
+      const size_t need = (size_t)net->max_batch * bi.H * bi.W * op.pack_cin * 2;
+      if (need > net->pack_scratch_bytes) net->pack_scratch_bytes = need;
+    }
+    if (net->pack_scratch_bytes) NIB_CUDA(cudaMalloc(&net->pack_scratch, net->pack_scratch_bytes + 256));
     for (auto& op : net->ops) {
       if (op.kind != 0) continue;
       ConvParams p;
+      if (op.pack_cin) {
+        fill_packed_conv_params(net, op, net->max_batch, &p);
+        if (tc_conv_supported(p)) {
+          int rc = tc_conv_plan_create(p, net->max_batch, &op.plan);
+          if (rc != NIB_OK) return rc;
+        } else {
+          op.pack_cin = 0;
+        }
+        continue;
+      }
       fill_conv_params(net, op, net->max_batch, &p);
       if (tc_conv_supported(p)) {
         int rc = tc_conv_plan_create(p, net->max_batch, &op.plan);
@@ -303,7 +356,16 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
       ConvParams p;
       fill_conv_params(net, op, N, &p);
       int rc;
-      if (op.plan && net->use_tc) {
+      if (op.plan && net->use_tc && op.pack_cin) {
+        const NetBuffer& bi = net->bufs[op.cd.in_buf];
+        rc = launch_bnrelu_pack(bi.ptr, bi.C, op.cd.in_coff, op.cd.Cin, op.pack_cin, op.d_pre_scale, op.d_pre_shift,
+                                net->pack_scratch, (long long)N * bi.H * bi.W, st);
+        net->launches++;
+        if (rc != NIB_OK) return rc;
+        fill_packed_conv_params(net, op, N, &p);
+        rc = tc_conv_launch(op.plan, p, st);
+        net->tc_launches++;
+      } else if (op.plan && net->use_tc) {
         rc = tc_conv_launch(op.plan, p, st);
         net->tc_launches++;
       } else {

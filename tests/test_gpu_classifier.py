@@ -261,7 +261,10 @@ def test_densenet121_bf16(nib):
     m = ocls.build_imagenet_model("densenet121")
     x = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(4, 1, 1, 1)
     x = x * torch.rand(4, 1, 1, 1, generator=torch.Generator().manual_seed(1))
-    _check_net(nib, m, x, "bf16", TOL_BF16)
+    net, got, want = _check_net(nib, m, x, "bf16", TOL_BF16)
+    total, tc = net.launch_counts()
+    # stem + 58 bottleneck 1x1 (BN-ReLU packed into a scratch tensor first) + 58 3x3 + 3 transitions
+    assert tc >= 118, f"only {tc} tcgen05 launches for DenseNet-121 (expected 120 convs on the tensor path)"
 
 
 def test_densenet_cifar_fp32(nib):
