@@ -55,6 +55,14 @@ struct TcKernelParams {
   int pf_dist;      // v2: L2-prefetch the operands of the tile this many iterations ahead (0 = off)
   unsigned int* err_flag;
   unsigned long long* dbg;   // NIB_TC_DBG=1: per-CTA role timers (cycles), 16 slots per CTA; null in production
+  // v3 L2 prefetch by the (mostly idle) epilogue warps: the activation rows / residual rows of the tile this CTA will
+  // work on two tiles from now, so the producer's TMA loads hit L2 instead of paying the DRAM round trip with a ring
+  // that holds well under one tile.  1x1 stride-1 layers only (rows are contiguous channel vectors).
+  int k_rot;                 // v3: CTA pair i starts its K loop at block (i * k_rot) % num_k_blocks (0: everyone at block 0)
+  const char* pf_a;          // first byte of the activation matrix slice (row 0, channel in_coff); null: off
+  long long pf_a_pitch;      // bytes between rows
+  int pf_a_lines;            // 128 B lines per row (Cin * 2 / 128)
+  long long pf_res_pitch;    // residual rows (p.res + res_coff is row 0)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -704,11 +712,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //   * the tile order keeps the CTA pairs that share activation rows adjacent in time (n fastest).
 static constexpr int TC3_THREADS = 64 + 256;
 
-template <int BLOCK_N, int STAGES, bool HAS_RES>
+// BRES: the layer's whole weight matrix (Cout == BLOCK_N, <= 9 K blocks: the 64-channel layers and the stem) is loaded
+// once per CTA and stays resident; the ring then carries activation tiles only, which halves the TMA instructions
+// the producer has to issue per K block (the issue rate, not the bytes, bounds these layers).
+static constexpr int TC3_BRES_KBLOCKS = 9;
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
 struct Tc3Smem {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
   static constexpr int BH_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;   // this CTA's half of the weight tile
-  static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + (BRES ? 0 : BH_BYTES);
+  static constexpr int BRES_BYTES = BRES ? TC3_BRES_KBLOCKS * BH_BYTES : 0;
   static constexpr int NBOX = BLOCK_N / 64;                          // 64-channel output boxes per tile
   static constexpr bool SPLIT_COLS = NBOX >= 2;                      // warpgroup g drains columns [g*BLOCK_N/2, ...) of every
                                                                      // tile; BLOCK_N = 64: warpgroup g drains the tiles in TMEM buffer g
@@ -717,10 +730,11 @@ struct Tc3Smem {
   static constexpr int BOX_BYTES = TC_BLOCK_M * 128;
   static constexpr int RSETS = HAS_RES ? (BLOCK_N == 256 ? 1 : 2) : 1;
   static constexpr int NBUF = HAS_RES ? RSETS * NBOX : 2;            // residual/output boxes, or 8 x 4 KB per-warp staging
-  static constexpr int BOX_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BOX_OFFSET = BRES_OFFSET + BRES_BYTES;
   static constexpr int BIAS_OFFSET = BOX_OFFSET + NBUF * BOX_BYTES;   // [warpgroup][2][CW] floats: the tile's folded-BN bias
   static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * 2 * CW * 4;
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF + 1;
   static constexpr int EMPTY_ARRIVALS = SPLIT_COLS ? 16 : 8;         // epilogue warps (both CTAs) that drain one accumulator
   // dynamic smem is the only shared allocation of the kernel, so it starts 1024-aligned in the CTA window; the kernel
   // checks that (the 128B swizzle needs it) instead of spending 1 KB of slack on it
@@ -843,12 +857,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_pair() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES>
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutTail,
                 const __grid_constant__ CUtensorMap tmRes, const TcKernelParams p) {
-  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES>;
+  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) {
@@ -862,6 +876,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); }; // used in the leader CTA
   auto res_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
   auto box_free_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + SM::NBUF + b); };
+  const uint32_t bres_full_bar = bar_base + 8u * (2 * STAGES + 4 + 2 * SM::NBUF);   // used in the leader CTA
   const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   auto box_addr = [&](int buf) { return smem_base + SM::BOX_OFFSET + (uint32_t)buf * SM::BOX_BYTES; };
@@ -907,6 +922,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(res_full_bar(b), 1);
       mbar_init(box_free_bar(b), 4);   // the four warps that store a box hand it back
     }
+    mbar_init(bres_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -933,8 +949,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     int it = 0;
     const uint32_t lbar0 = mapa_shared(full_bar(0), 0);   // leader CTA's full barriers
-    const uint32_t tx_bytes = (uint32_t)(2 * (p.a_bytes + SM::BH_BYTES));
+    const uint32_t tx_bytes = (uint32_t)(2 * (p.a_bytes + (BRES ? 0 : SM::BH_BYTES)));
     const int b_row0 = (int)rank * (BLOCK_N / 2);
+    const int krot0 = (int)(((long long)pair * p.k_rot) % p.num_k_blocks);
     // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
     // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
     // busy epilogue never stalls the operand ring
@@ -958,6 +975,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     };
     if (dbg_on) t_loop0 = clock64();
+    if (BRES) {   // both CTAs fetch their half of every K block of the weights once
+      if (elect_one()) {
+        const uint32_t lb = mapa_shared(bres_full_bar, 0);
+        if (rank == 0) mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(2 * p.num_k_blocks * SM::BH_BYTES));
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          tma2_load_2d(smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES, &tmB, lb, kb * TC_BLOCK_K, b_row0);
+      }
+      __syncwarp();
+    }
     for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
@@ -975,8 +1001,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         img = m_tile / p.P;
         h0 = (m_tile - img * p.P) * p.stride;
       }
-      int cb = 0, tap_s = 0, tap_r = 0;   // k-block -> (filter row, filter column, 64-channel block), kept incrementally
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      // Every CTA pair walks K from a different starting block: the pairs run in lock step, and with a common order all
+      // 74 of them ask L2 for the same weight lines at the same moment.  fp32 accumulation order differs per pair only.
+      int kb = krot0;
+      int cb = kb % p.cblocks, tap_s = (kb / p.cblocks) % p.S, tap_r = (kb / p.cblocks) / p.S;   // k-block -> (filter row, column, 64-channel block)
+      for (int kk = 0; kk < p.num_k_blocks; ++kk) {
         if (HAS_RES) issue_pending(false);
         TC3_TIMED(0, mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1));
         if (elect_one()) {
@@ -991,11 +1020,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             tma2_load_2d(a_dst, &tmA, lbar, c0, m0);
           }
-          tma2_load_2d(a_dst + SM::A_BYTES, &tmB, lbar, kb * TC_BLOCK_K, n0 + b_row0);
+          if (!BRES) tma2_load_2d(a_dst + SM::A_BYTES, &tmB, lbar, kb * TC_BLOCK_K, n0 + b_row0);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        if (++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
+        if (++kb == p.num_k_blocks) { kb = 0; cb = 0; tap_s = 0; tap_r = 0; }
+        else if (++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
       }
       if (HAS_RES) {
         issue_pending(true);   // the tile before this one: its boxes were freed at least one whole tile ago
@@ -1019,27 +1049,32 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const int krot0 = (int)(((long long)pair * p.k_rot) % p.num_k_blocks);
       if (dbg_on) t_loop0 = clock64();
+      if (BRES) mbar_wait(bres_full_bar, 0, p.err_flag, 7);
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
         const int ab = it & 1;
         TC3_TIMED(1, mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        int kb = krot0;
+        for (int kk = 0; kk < p.num_k_blocks; ++kk) {
           TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
             const uint64_t adesc = make_smem_desc_sw128(a_addr);
-            const uint64_t bdesc = make_smem_desc_sw128(a_addr + SM::A_BYTES);
+            const uint64_t bdesc = make_smem_desc_sw128(BRES ? smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES
+                                                             : a_addr + SM::A_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-              umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
             umma2_commit_both(empty_bar(stage));
-            if (kb == p.num_k_blocks - 1) umma2_commit_both(tmem_full_bar(ab));
+            if (kk == p.num_k_blocks - 1) umma2_commit_both(tmem_full_bar(ab));
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++kb == p.num_k_blocks) kb = 0;
         }
       }
       if (dbg_on && lane == 0) {
@@ -1073,6 +1108,33 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // one tile ahead into a register, parked in smem and read back as broadcast LDS.128.
     float bias_pre = 0.f;
     if (has_bias && wt < SM::CW && tile < total_tiles) bias_pre = __ldg(p.bias + (tile % p.n_tiles) * BLOCK_N + colbase + wt);
+    // L2 prefetch of a future tile's DRAM-resident operands (see TcKernelParams::pf_a)
+    auto prefetch_tile = [&](int ft) {
+      if (ft >= total_tiles) return;
+      const int fn = ft % p.n_tiles;
+      const int fm0 = ((ft / p.n_tiles) * 2 + (int)rank) * TC_BLOCK_M;
+      if (p.pf_a != nullptr) {
+        // the n-tiles that share these activation rows run on other CTA pairs at the same time: split the rows
+        const int rows_per = p.n_tiles <= TC_BLOCK_M ? TC_BLOCK_M / p.n_tiles : 1;
+        const int r0 = fn * rows_per;
+        const int nlines = (fn < TC_BLOCK_M ? rows_per : 0) * p.pf_a_lines;
+        for (int l = wt + (SM::SPLIT_COLS ? g * 128 : 0); l < nlines; l += (SM::SPLIT_COLS ? 256 : 128)) {
+          const int row = fm0 + r0 + l / p.pf_a_lines;
+          if (row < p.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_a + (long long)row * p.pf_a_pitch + (l % p.pf_a_lines) * 128));
+        }
+      }
+      if (HAS_RES && p.pf_res_pitch != 0) {
+        constexpr int RL = BLOCK_N * 2 / 128;   // lines per residual row of this tile
+        const char* rbase = reinterpret_cast<const char*>(p.res) + (size_t)(p.res_coff + fn * BLOCK_N) * 2;
+        for (int l = wt + (SM::SPLIT_COLS ? g * 128 : 0); l < TC_BLOCK_M * RL; l += (SM::SPLIT_COLS ? 256 : 128)) {
+          const int row = fm0 + l / RL;
+          if (row < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase + (long long)row * p.pf_res_pitch + (l % RL) * 128));
+        }
+      }
+    };
+    const bool pf_on = p.pf_a != nullptr || (HAS_RES && p.pf_res_pitch != 0);
+    if (pf_on) prefetch_tile(tile + step);
     if (dbg_on) t_loop0 = clock64();
     for (; tile < total_tiles; tile += step, it += (SM::SPLIT_COLS ? 1 : 2), ++lt) {
       const int n_tile = tile % p.n_tiles;
@@ -1080,6 +1142,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m0 = m_tile * p.tile_rows;
       const int n0 = n_tile * BLOCK_N;
       const int ab = it & 1;
+      if (pf_on) prefetch_tile(tile + 2 * step);
       TC3_TIMED(0, mbar_wait(tmem_full_bar(ab), (uint32_t)((it >> 1) & 1), p.err_flag, 3));
       tc_fence_after();
       const uint32_t bias_s = bias_wg + (uint32_t)((lt & 1) * SM::CW * 4);
@@ -1440,13 +1503,13 @@ static int launch_tc2(const TcConvPlan* plan, const TcKernelParams& kp, int tile
   return NIB_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES>
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
 static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStream_t st) {
-  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES>;
+  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
   static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static bool attr_set = false;
   if (!attr_set) {
-    NIB_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES>,
+    NIB_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES, BRES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
@@ -1469,7 +1532,7 @@ static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl && cap == cudaStreamCaptureStatusNone && kp.dbg == nullptr) ? 1 : 0;
-  NIB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES>, plan->tmA, plan->tmBh, plan->tmOut32,
+  NIB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES, BRES>, plan->tmA, plan->tmBh, plan->tmOut32,
                               plan->tmOutTail, plan->tmRes, kp));
   return NIB_OK;
 }
@@ -1480,6 +1543,9 @@ static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int til
     const bool res = kp.res != nullptr;
     if (plan->block_n == 256) return res ? launch_tc3<256, 5, true>(plan, kp, st) : launch_tc3<256, 6, false>(plan, kp, st);
     if (plan->block_n == 128) return res ? launch_tc3<128, 6, true>(plan, kp, st) : launch_tc3<128, 8, false>(plan, kp, st);
+    static const bool no_bres = getenv("NIB_TC_NO_BRES") != nullptr;
+    if (plan->block_n == 64 && !res && kp.n_tiles == 1 && kp.num_k_blocks <= TC3_BRES_KBLOCKS && !no_bres)
+      return launch_tc3<64, 9, false, true>(plan, kp, st);   // resident weights: stem, 56x56 64-channel layers
     if (plan->block_n == 64) return res ? launch_tc3<64, 9, true>(plan, kp, st) : launch_tc3<64, 9, false>(plan, kp, st);
   }
   if (plan->v2 && !kp.out_f32) {
@@ -1588,6 +1654,20 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
     static int pf = -1;
     if (pf < 0) { const char* e = getenv("NIB_TC_PF"); pf = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/README.md), off by default
     kp.pf_dist = pf;
+  }
+  {
+    static int krot = -1;
+    if (krot < 0) { const char* e = getenv("NIB_TC_KROT"); krot = e ? atoi(e) : 0; }   // measured: no gain from de-synchronising the pairs; default keeps one K order
+    kp.k_rot = krot;
+  }
+  static const bool no_pf = getenv("NIB_TC_L2PF") == nullptr;   // measured: no gain (profiles/README.md); opt-in
+  if (plan->v3 && !no_pf && plan->tile_rows == TC_BLOCK_M) {
+    if (plan->im2col == 0 && (p.Cin * 2) % 128 == 0) {
+      kp.pf_a = reinterpret_cast<const char*>(p.in) + (size_t)p.in_coff * 2;
+      kp.pf_a_pitch = (long long)p.in_cstride * 2;
+      kp.pf_a_lines = p.Cin * 2 / 128;
+    }
+    kp.pf_res_pitch = (long long)p.res_cstride * 2;
   }
   const int tiles = kp.m_tiles * kp.n_tiles;
   static const bool dbg = getenv("NIB_TC_DBG") != nullptr;
