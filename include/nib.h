@@ -237,6 +237,11 @@ int nib_gp_gram_rbf(const double* d_Xa, int na, const double* d_Xb, int nb, int 
  * (_gpr.py:352). */
 int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream);
 
+/* Diagnostic hook: C[M,N] -= A[M,K] * B[K,N] (row-major fp64) through the GEMM the blocked Cholesky / TRSM trailing
+ * updates use (gp.cu dgemm_sub_kernel).  No reference counterpart; used by tools/gp_profile.py to measure the kernel
+ * against the fp64 peak. */
+int nib_gp_dgemm_sub(const double* d_A, const double* d_B, double* d_C, int M, int N, int K, void* stream);
+
 /* Triangular solves with the lower factor L ([n][ldl]) on B ([n][ldb], nrhs columns), in place.
  * trans=0: B <- L^{-1} B ;  trans=1: B <- L^{-T} B.   (cho_solve = trans 0 then trans 1) */
 int nib_gp_trsm(const double* d_L, int n, int ldl, double* d_B, int nrhs, int ldb, int trans,

@@ -81,6 +81,7 @@ _PROTOTYPES = {
     "nib_gp_gram_rbf": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _i, _vp, _i, _vp]),
     "nib_gp_cholesky": (_i, [_vp, _i, _i, _vp, _vp]),
     "nib_gp_trsm": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp]),
+    "nib_gp_dgemm_sub": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "nib_gp_posterior": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "nib_gp_lml": (_i, [_vp, _i, _i, _vp, _vp, C.POINTER(_d), _vp]),
     "nib_gp_lml_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, C.POINTER(_d), _vp]),

@@ -85,80 +85,115 @@ struct DgemmArgs {
   int lower_only;
 };
 
-static constexpr int GT = 128, GK = 8;
+// 128 x 128 output tile per block, 16-deep K chunks, 8 warps (2 x 4) each accumulating a 64 x 32 sub-tile with the fp64
+// tensor-core instruction mma.sync.m8n8k4 (32 MMA tiles, 64 accumulator doubles per thread): per 4-deep K step a warp
+// issues 12 shared-memory fragment loads for 32 MMAs.  B200's fp64 rate sits behind the tensor pipe: the CUDA-core DFMA
+// version of this kernel measured 9 TFLOP/s (profiles/README.md).  The next chunk's global loads are issued into
+// registers before the current chunk's MMAs, so DRAM / L2 latency is covered by arithmetic instead of by occupancy.
+static constexpr int GT = 128, GK = 16, GS = GT + 4;   // GS: smem row pitch, = 8 words mod 32 -> conflict-free fragments
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
 dgemm_sub_kernel(DgemmArgs g) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (g.lower_only && bj > bi) return;
-  __shared__ __align__(16) double As[GK][GT];
-  __shared__ __align__(16) double Bs[GK][GT];
+  __shared__ __align__(16) double As[GK][GS];
+  __shared__ __align__(16) double Bs[GK][GS];
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3;          // warp tile: rows wm*64.., cols wn*32..
+  const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates (groupID, threadID_in_group)
   const int i0 = bi * GT, j0 = bj * GT;
-  double acc[8][8];
+  double acc[8][4][2];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  // loader mapping: 1024 elements each for A and B per chunk, 4 per thread.
-  // choose the fastest-varying thread index along the unit-stride direction.
+  // loader mapping: 128 x 16 elements each for A and B per chunk, 8 per thread; the fastest-varying thread index runs
+  // along the unit-stride direction of the operand so a warp reads whole 128 B lines.
   const bool a_t_fast = (g.sat == 1);
   const bool b_j_fast = (g.sbj == 1);
-
-  for (int k0 = 0; k0 < g.K; k0 += GK) {
-    double av[4], bv[4];
+  double av[8], bv[8];
+  auto a_pos = [&](int e, int& ii, int& tt) {
+    const int idx = tid + e * 256;
+    if (a_t_fast) { tt = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GT - 1); tt = idx >> 7; }
+  };
+  auto b_pos = [&](int e, int& jj, int& tt) {
+    const int idx = tid + e * 256;
+    if (b_j_fast) { jj = idx & (GT - 1); tt = idx >> 7; } else { tt = idx & (GK - 1); jj = idx >> 4; }
+  };
+  auto load_chunk = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;
-      int ii, tt;
-      if (a_t_fast) { tt = idx & (GK - 1); ii = idx >> 3; } else { ii = idx & (GT - 1); tt = idx >> 7; }
+    for (int e = 0; e < 8; ++e) {
+      int ii, tt, jj, t2;
+      a_pos(e, ii, tt);
+      b_pos(e, jj, t2);
       const int gi = i0 + ii, gt = k0 + tt;
       av[e] = (gi < g.M && gt < g.K) ? g.A[gi * g.sai + gt * g.sat] : 0.0;
-      int jj, t2;
-      if (b_j_fast) { jj = idx & (GT - 1); t2 = idx >> 7; } else { t2 = idx & (GK - 1); jj = idx >> 3; }
       const int gj = j0 + jj, gt2 = k0 + t2;
       bv[e] = (gj < g.N && gt2 < g.K) ? g.B[gt2 * g.sbt + gj * g.sbj] : 0.0;
     }
-    __syncthreads();
+  };
+  load_chunk(0);
+  for (int k0 = 0; k0 < g.K; k0 += GK) {
+    __syncthreads();   // everyone is done reading the previous chunk
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;
-      int ii, tt;
-      if (a_t_fast) { tt = idx & (GK - 1); ii = idx >> 3; } else { ii = idx & (GT - 1); tt = idx >> 7; }
+    for (int e = 0; e < 8; ++e) {
+      int ii, tt, jj, t2;
+      a_pos(e, ii, tt);
+      b_pos(e, jj, t2);
       As[tt][ii] = av[e];
-      int jj, t2;
-      if (b_j_fast) { jj = idx & (GT - 1); t2 = idx >> 7; } else { t2 = idx & (GK - 1); jj = idx >> 3; }
       Bs[t2][jj] = bv[e];
     }
     __syncthreads();
+    if (k0 + GK < g.K) load_chunk(k0 + GK);
 #pragma unroll
-    for (int t = 0; t < GK; ++t) {
-      double a[8], b[8];
+    for (int t = 0; t < GK; t += 4) {
+      double a[8], b[4];
 #pragma unroll
-      for (int u = 0; u < 8; u += 2) {
-        const double2 a2 = *reinterpret_cast<const double2*>(&As[t][ty * 8 + u]);
-        a[u] = a2.x; a[u + 1] = a2.y;
-        const double2 b2 = *reinterpret_cast<const double2*>(&Bs[t][tx * 8 + u]);
-        b[u] = b2.x; b[u + 1] = b2.y;
-      }
+      for (int mt = 0; mt < 8; ++mt) a[mt] = As[t + fk][wm * 64 + mt * 8 + fr];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[t + fk][wn * 32 + nt * 8 + fr];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+      for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
     }
   }
+  // C -= acc.  The loads are gathered into registers in batches of 16 before any store of the batch: written as one
+  // read-modify-write per element the compiler must assume every store may alias the next load and serialises 64
+  // L2 round trips per thread (that, not the arithmetic, was 70 % of the tile time of the first version).
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int i = i0 + ty * 8 + u;
-    if (i >= g.M) continue;
+  for (int mb = 0; mb < 8; mb += 2) {
+    double cv[2][4][2];
 #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      const int j = j0 + tx * 8 + v;
-      if (j >= g.N) continue;
-      if (g.lower_only && j > i) continue;
-      g.C[i * g.ldc + j] -= acc[u][v];
+    for (int m2 = 0; m2 < 2; ++m2) {
+      const int i = i0 + wm * 64 + (mb + m2) * 8 + fr;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = j0 + wn * 32 + nt * 8 + 2 * fk + c;
+          const bool ok = i < g.M && j < g.N && !(g.lower_only && j > i);
+          cv[m2][nt][c] = ok ? g.C[i * g.ldc + j] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int m2 = 0; m2 < 2; ++m2) {
+      const int i = i0 + wm * 64 + (mb + m2) * 8 + fr;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = j0 + wn * 32 + nt * 8 + 2 * fk + c;
+          const bool ok = i < g.M && j < g.N && !(g.lower_only && j > i);
+          if (ok) g.C[i * g.ldc + j] = cv[m2][nt][c] - acc[mb + m2][nt][c];
+        }
     }
   }
 }
@@ -172,52 +207,77 @@ static int dgemm_sub(const DgemmArgs& g, cudaStream_t st) {
 }
 
 // ---- Cholesky --------------------------------------------------------------------------------
-// factor the nb x nb diagonal block at (k0,k0) in shared memory
+// Factor the nb x nb (<= 64) diagonal block at (k0,k0).  The block lives in registers: thread (br, bc) of a 16 x 16
+// grid owns the 4 x 4 sub-block (rows 4br.., cols 4bc..); each of the 64 elimination steps publishes one column
+// through a double-buffered 64-entry smem vector, so a step costs one __syncthreads and 16 predicated FMAs per thread
+// (right-looking, the update order of LAPACK dpotf2 that scipy.linalg.cholesky ends in, _gpr.py:352).
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restrict__ info) {
-  __shared__ double s[NB][NB + 1];
+  __shared__ double colbuf[2][NB];
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < nb * nb; idx += 256) {
-    int i = idx / nb, j = idx - i * nb;
-    s[i][j] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
-  }
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    const double d = s[j][j];
-    if (!(d > 0.0)) {  // also catches NaN
-      if (tid == 0 && *info == 0) *info = k0 + j + 1;
-      return;
+  const int br = tid >> 4, bc = tid & 15;
+  double r[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = 4 * br + a, j = 4 * bc + b;
+      r[a][b] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : ((i == j) ? 1.0 : 0.0);   // identity padding
     }
-    const double r = sqrt(d);
-    __syncthreads();
-    if (tid == 0) s[j][j] = r;
-    for (int i = j + 1 + tid; i < nb; i += 256) s[i][j] = s[i][j] / r;
-    __syncthreads();
-    // trailing update of the lower triangle: (i, k) with j < k <= i
-    const int rem = nb - j - 1;
-    for (int idx = tid; idx < rem * rem; idx += 256) {
-      const int ii = idx / rem, kk = idx - ii * rem;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        s[i][k] -= s[i][j] * s[k][j];
+  for (int j = 0; j < NB; ++j) {
+    const int cb = j >> 2, cj = j & 3;
+    double* col = colbuf[j & 1];
+    if (bc == cb) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double v = r[a][0];
+        if (cj == 1) v = r[a][1];
+        if (cj == 2) v = r[a][2];
+        if (cj == 3) v = r[a][3];
+        col[4 * br + a] = v;
       }
     }
     __syncthreads();
+    const double d = col[j];
+    if (!(d > 0.0)) {  // also catches NaN; uniform across the block
+      if (tid == 0 && *info == 0) *info = k0 + j + 1;
+      return;
+    }
+    const double rs = sqrt(d);
+    const double inv = 1.0 / rs;
+    double lr[4], lc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      lr[a] = col[4 * br + a] * inv;
+      lc[a] = col[4 * bc + a] * inv;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * br + a, k = 4 * bc + b;
+        if (k > j && i >= k) r[a][b] = fma(-lr[a], lc[b], r[a][b]);
+        if (k == j) r[a][b] = (i > j) ? lr[a] : ((i == j) ? rs : r[a][b]);
+      }
   }
-  for (int idx = tid; idx < nb * nb; idx += 256) {
-    int i = idx / nb, j = idx - i * nb;
-    if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = s[i][j];
-  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = 4 * br + a, j = 4 * bc + b;
+      if (i < nb && j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = r[a][b];
+    }
 }
 
-// rows below the diagonal block: solve X * Lkk^T = A[i, k0:k0+nb], one row per thread
+// rows below the diagonal block: solve X * Lkk^T = A[i, k0:k0+nb], one row per thread; four interleaved partial sums
+// keep four independent FMA chains in flight (the single-chain version is bound by the fp64 FMA latency)
 __global__ void __launch_bounds__(128)
 trsm_panel_kernel(double* __restrict__ A, int ld, int k0, int nb, int n, const int* __restrict__ info) {
   __shared__ double L[NB][NB + 1];
   if (*info != 0) return;
-  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
-    int i = idx / nb, j = idx - i * nb;
-    L[i][j] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    int i = idx / NB, j = idx - i * NB;
+    L[i][j] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : ((i == j) ? 1.0 : 0.0);
   }
   __syncthreads();
   const int i = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,12 +288,17 @@ trsm_panel_kernel(double* __restrict__ A, int ld, int k0, int nb, int n, const i
   for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? row[j] : 0.0;
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    if (j < nb) {
-      double sacc = x[j];
+    double s0 = x[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-      for (int t = 0; t < j; ++t) sacc = fma(-x[t], L[j][t], sacc);
-      x[j] = sacc / L[j][j];
+    for (int t = 0; t + 3 < j; t += 4) {
+      s0 = fma(-x[t], L[j][t], s0);
+      s1 = fma(-x[t + 1], L[j][t + 1], s1);
+      s2 = fma(-x[t + 2], L[j][t + 2], s2);
+      s3 = fma(-x[t + 3], L[j][t + 3], s3);
     }
+#pragma unroll
+    for (int t = j & ~3; t < j; ++t) s0 = fma(-x[t], L[j][t], s0);
+    x[j] = ((s0 + s1) + (s2 + s3)) / L[j][j];
   }
 #pragma unroll
   for (int j = 0; j < NB; ++j)
@@ -256,10 +321,17 @@ trsm_diag_fwd_kernel(const double* __restrict__ Lm, int ldl, double* __restrict_
 #pragma unroll
   for (int r = 0; r < NB; ++r) {
     if (r < nb) {
-      double sacc = B[(size_t)(k0 + r) * ldb + c];
+      double s0 = B[(size_t)(k0 + r) * ldb + c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-      for (int t = 0; t < r; ++t) sacc = fma(-L[r][t], x[t], sacc);
-      x[r] = sacc / L[r][r];
+      for (int t = 0; t + 3 < r; t += 4) {
+        s0 = fma(-L[r][t], x[t], s0);
+        s1 = fma(-L[r][t + 1], x[t + 1], s1);
+        s2 = fma(-L[r][t + 2], x[t + 2], s2);
+        s3 = fma(-L[r][t + 3], x[t + 3], s3);
+      }
+#pragma unroll
+      for (int t = r & ~3; t < r; ++t) s0 = fma(-L[r][t], x[t], s0);
+      x[r] = ((s0 + s1) + (s2 + s3)) / L[r][r];
       B[(size_t)(k0 + r) * ldb + c] = x[r];
     }
   }
@@ -290,38 +362,163 @@ trsm_diag_bwd_kernel(const double* __restrict__ Lm, int ldl, double* __restrict_
   }
 }
 
+// ---- single right-hand side (alpha = K^-1 y, _gpr.py:363-367) ----------------------------------
+// One launch per 64-row block of L.  Every thread block re-solves the 64 x 64 diagonal system in its first warp (64
+// shuffle-broadcast steps, cheaper than a grid-wide dependency) and then applies the block column / block row of L to
+// its own slice of the remaining vector: a streaming GEMV, L is read exactly once per solve.
+__device__ __forceinline__ void trsv_diag_warp(const double (*Ls)[NB + 1], double* xs, int nb, bool transposed) {
+  // warp 0: lane owns entries lane and lane + 32 of the block's right-hand side (already in xs)
+  const int lane = threadIdx.x;
+  double b0 = xs[lane], b1 = xs[lane + 32];
+  if (!transposed) {
+    for (int j = 0; j < NB; ++j) {
+      const double bj = __shfl_sync(0xffffffffu, j < 32 ? b0 : b1, j & 31);
+      const double xj = bj / Ls[j][j];
+      if (lane == (j & 31)) { if (j < 32) b0 = xj; else b1 = xj; }
+      if (lane > j) b0 = fma(-Ls[lane][j], xj, b0);
+      if (lane + 32 > j) b1 = fma(-Ls[lane + 32][j], xj, b1);
+    }
+  } else {
+    for (int j = NB - 1; j >= 0; --j) {
+      const double bj = __shfl_sync(0xffffffffu, j < 32 ? b0 : b1, j & 31);
+      const double xj = bj / Ls[j][j];
+      if (lane == (j & 31)) { if (j < 32) b0 = xj; else b1 = xj; }
+      if (lane < j) b0 = fma(-Ls[j][lane], xj, b0);
+      if (lane + 32 < j) b1 = fma(-Ls[j][lane + 32], xj, b1);
+    }
+  }
+  (void)nb;
+  xs[lane] = b0;
+  xs[lane + 32] = b1;
+}
+
+__global__ void __launch_bounds__(256)
+trsv_step_kernel(const double* __restrict__ Lm, int ldl, double* __restrict__ b, double* __restrict__ x, int n, int k0,
+                 int nb, int trans) {
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double xs[NB];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int i = idx / NB, j = idx - i * NB;
+    Ls[i][j] = (i < nb && j <= i) ? Lm[(size_t)(k0 + i) * ldl + k0 + j] : ((i == j) ? 1.0 : 0.0);
+  }
+  if (tid < NB) xs[tid] = tid < nb ? b[k0 + tid] : 0.0;
+  __syncthreads();
+  if (tid < 32) trsv_diag_warp(Ls, xs, nb, trans != 0);
+  __syncthreads();
+  // the solved entries go to a separate vector: blocks of this launch that start late must still read the unsolved b
+  if (blockIdx.x == 0 && tid < nb) x[k0 + tid] = xs[tid];
+  if (!trans) {
+    // rows below the block: b[i] -= L[i][k0 .. k0+nb) . x   (one warp per row, lanes along the 64 columns)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = k0 + nb + blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+      const double* row = Lm + (size_t)i * ldl + k0;
+      double acc = row[lane] * xs[lane];
+      if (lane + 32 < nb) acc = fma(row[lane + 32], xs[lane + 32], acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) b[i] -= acc;
+    }
+  } else {
+    // columns left of the block: b[j] -= sum_t L[k0+t][j] * x[t]   (one thread per column, coalesced along j)
+    for (int j = blockIdx.x * 256 + tid; j < k0; j += gridDim.x * 256) {
+      double acc = 0.0;
+      for (int t = 0; t < nb; ++t) acc = fma(Lm[(size_t)(k0 + t) * ldl + j], xs[t], acc);
+      b[j] -= acc;
+    }
+  }
+}
+
+static double* g_trsv_x = nullptr;
+static size_t g_trsv_cap = 0;
+static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, cudaStream_t st) {
+  if (g_trsv_cap < (size_t)n) {
+    if (g_trsv_x) cudaFree(g_trsv_x);
+    g_trsv_cap = (size_t)n < 16384 ? 16384 : (size_t)n;
+    NIB_CUDA(cudaMalloc(&g_trsv_x, g_trsv_cap * sizeof(double)));
+  }
+  const int nblk = ceil_div(n, NB);
+  for (int s = 0; s < nblk; ++s) {
+    const int blk = trans ? nblk - 1 - s : s;
+    const int k0 = blk * NB;
+    const int nb = min(NB, n - k0);
+    const int work = trans ? ceil_div(k0, 256) : ceil_div(n - (k0 + nb), 8);
+    int grid = work < 1 ? 1 : work;
+    if (grid > 4 * num_sms()) grid = 4 * num_sms();
+    trsv_step_kernel<<<grid, 256, 0, st>>>(L, ldl, b, g_trsv_x, n, k0, nb, trans);
+    NIB_LAUNCH_CHECK();
+  }
+  NIB_CUDA(cudaMemcpyAsync(b, g_trsv_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return NIB_OK;
+}
+
+// Two-level blocking: 64-wide steps (diagonal solves, one column per thread) inside 256-wide super-blocks.  Inside a
+// super-block the rank-64 updates only touch the super-block's own rows; everything outside gets ONE rank-256 update
+// per super-block.  The trailing GEMM is read-modify-write on its output: at K = 64 it measured 8-9 TFLOP/s (the tile's
+// C round trip dominates), at K = 256 17 TFLOP/s, at large K 25.7 of the 37 TFLOP/s DMMA peak (tools/gp_profile.py).
+static constexpr int NBO = 256;
+
 static int trsm_impl(const double* L, int n, int ldl, double* B, int nrhs, int ldb, int trans, cudaStream_t st) {
   if (n <= 0 || nrhs <= 0) return NIB_OK;
+  if (nrhs == 1 && ldb == 1) return trsv_impl(L, n, ldl, B, trans, st);
   const int cb = ceil_div(nrhs, 128);
+  DgemmArgs g;
+  g.lower_only = 0;
+  g.N = nrhs;
+  g.ldc = ldb;
+  g.sbt = ldb; g.sbj = 1;
   if (!trans) {
-    for (int k0 = 0; k0 < n; k0 += NB) {
-      const int nb = min(NB, n - k0);
-      trsm_diag_fwd_kernel<<<cb, 128, 0, st>>>(L, ldl, B, ldb, nrhs, k0, nb);
-      NIB_LAUNCH_CHECK();
-      const int below = n - (k0 + nb);
+    for (int K0 = 0; K0 < n; K0 += NBO) {
+      const int W = min(NBO, n - K0);
+      for (int k0 = K0; k0 < K0 + W; k0 += NB) {
+        const int nb = min(NB, K0 + W - k0);
+        trsm_diag_fwd_kernel<<<cb, 128, 0, st>>>(L, ldl, B, ldb, nrhs, k0, nb);
+        NIB_LAUNCH_CHECK();
+        const int rest = K0 + W - (k0 + nb);   // remaining rows of this super-block
+        if (rest > 0) {
+          g.A = L + (size_t)(k0 + nb) * ldl + k0; g.sai = ldl; g.sat = 1;   // L[i][k0+t]
+          g.B = B + (size_t)k0 * ldb;                                        // X[t][j]
+          g.C = B + (size_t)(k0 + nb) * ldb;
+          g.M = rest; g.K = nb;
+          int rc = dgemm_sub(g, st);
+          if (rc != NIB_OK) return rc;
+        }
+      }
+      const int below = n - (K0 + W);
       if (below > 0) {
-        DgemmArgs g;
-        g.A = L + (size_t)(k0 + nb) * ldl + k0; g.sai = ldl; g.sat = 1;   // L[i][k0+t]
-        g.B = B + (size_t)k0 * ldb; g.sbt = ldb; g.sbj = 1;                // X[t][j]
-        g.C = B + (size_t)(k0 + nb) * ldb; g.ldc = ldb;
-        g.M = below; g.N = nrhs; g.K = nb; g.lower_only = 0;
+        g.A = L + (size_t)(K0 + W) * ldl + K0; g.sai = ldl; g.sat = 1;
+        g.B = B + (size_t)K0 * ldb;
+        g.C = B + (size_t)(K0 + W) * ldb;
+        g.M = below; g.K = W;
         int rc = dgemm_sub(g, st);
         if (rc != NIB_OK) return rc;
       }
     }
   } else {
-    const int nblk = ceil_div(n, NB);
-    for (int b = nblk - 1; b >= 0; --b) {
-      const int k0 = b * NB;
-      const int nb = min(NB, n - k0);
-      trsm_diag_bwd_kernel<<<cb, 128, 0, st>>>(L, ldl, B, ldb, nrhs, k0, nb);
-      NIB_LAUNCH_CHECK();
-      if (k0 > 0) {
-        DgemmArgs g;
-        g.A = L + (size_t)k0 * ldl; g.sai = 1; g.sat = ldl;                // A(i,t) = L[k0+t][i]
-        g.B = B + (size_t)k0 * ldb; g.sbt = ldb; g.sbj = 1;
-        g.C = B; g.ldc = ldb;
-        g.M = k0; g.N = nrhs; g.K = nb; g.lower_only = 0;
+    const int nsb = ceil_div(n, NBO);
+    for (int sb = nsb - 1; sb >= 0; --sb) {
+      const int K0 = sb * NBO;
+      const int W = min(NBO, n - K0);
+      const int nblk = ceil_div(W, NB);
+      for (int b = nblk - 1; b >= 0; --b) {
+        const int k0 = K0 + b * NB;
+        const int nb = min(NB, K0 + W - k0);
+        trsm_diag_bwd_kernel<<<cb, 128, 0, st>>>(L, ldl, B, ldb, nrhs, k0, nb);
+        NIB_LAUNCH_CHECK();
+        const int rest = k0 - K0;   // rows of this super-block above the block just solved
+        if (rest > 0) {
+          g.A = L + (size_t)k0 * ldl + K0; g.sai = 1; g.sat = ldl;          // A(i,t) = L[k0+t][K0+i]
+          g.B = B + (size_t)k0 * ldb;
+          g.C = B + (size_t)K0 * ldb;
+          g.M = rest; g.K = nb;
+          int rc = dgemm_sub(g, st);
+          if (rc != NIB_OK) return rc;
+        }
+      }
+      if (K0 > 0) {
+        g.A = L + (size_t)K0 * ldl; g.sai = 1; g.sat = ldl;                 // A(i,t) = L[K0+t][i]
+        g.B = B + (size_t)K0 * ldb;
+        g.C = B;
+        g.M = K0; g.K = W;
         int rc = dgemm_sub(g, st);
         if (rc != NIB_OK) return rc;
       }
@@ -542,25 +739,56 @@ int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream) {
   NIB_REQUIRE(d_K && d_info && n > 0 && ldk >= n, "nib_gp_cholesky: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   NIB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = min(NB, n - k0);
-    potrf_diag_kernel<<<1, 256, 0, st>>>(d_K, ldk, k0, nb, d_info);
-    NIB_LAUNCH_CHECK();
-    const int below = n - (k0 + nb);
-    if (below > 0) {
-      trsm_panel_kernel<<<ceil_div(below, 128), 128, 0, st>>>(d_K, ldk, k0, nb, n, d_info);
+  // right-looking, two-level: 64-wide panels inside 256-wide super-blocks (see trsm_impl for why)
+  for (int K0 = 0; K0 < n; K0 += NBO) {
+    const int W = min(NBO, n - K0);
+    for (int k0 = K0; k0 < K0 + W; k0 += NB) {
+      const int nb = min(NB, K0 + W - k0);
+      potrf_diag_kernel<<<1, 256, 0, st>>>(d_K, ldk, k0, nb, d_info);
       NIB_LAUNCH_CHECK();
+      const int below = n - (k0 + nb);
+      if (below > 0) {
+        trsm_panel_kernel<<<ceil_div(below, 128), 128, 0, st>>>(d_K, ldk, k0, nb, n, d_info);
+        NIB_LAUNCH_CHECK();
+      }
+      const int cols = K0 + W - (k0 + nb);   // columns of this super-block still to be factored
+      if (below > 0 && cols > 0) {
+        DgemmArgs g;
+        const double* X = d_K + (size_t)(k0 + nb) * ldk + k0;
+        g.A = X; g.sai = ldk; g.sat = 1;      // X[i][t]
+        g.B = X; g.sbt = 1; g.sbj = ldk;      // B(t,j) = X[j][t]
+        g.C = d_K + (size_t)(k0 + nb) * ldk + (k0 + nb); g.ldc = ldk;
+        g.M = below; g.N = cols; g.K = nb; g.lower_only = 1;
+        int rc = dgemm_sub(g, st);
+        if (rc != NIB_OK) return rc;
+      }
+    }
+    const int below = n - (K0 + W);
+    if (below > 0) {
       DgemmArgs g;
-      const double* X = d_K + (size_t)(k0 + nb) * ldk + k0;
-      g.A = X; g.sai = ldk; g.sat = 1;      // X[i][t]
-      g.B = X; g.sbt = 1; g.sbj = ldk;      // B(t,j) = X[j][t]
-      g.C = d_K + (size_t)(k0 + nb) * ldk + (k0 + nb); g.ldc = ldk;
-      g.M = below; g.N = below; g.K = nb; g.lower_only = 1;
+      const double* X = d_K + (size_t)(K0 + W) * ldk + K0;
+      g.A = X; g.sai = ldk; g.sat = 1;
+      g.B = X; g.sbt = 1; g.sbj = ldk;
+      g.C = d_K + (size_t)(K0 + W) * ldk + (K0 + W); g.ldc = ldk;
+      g.M = below; g.N = below; g.K = W; g.lower_only = 1;
       int rc = dgemm_sub(g, st);
       if (rc != NIB_OK) return rc;
     }
   }
   return NIB_OK;
+}
+
+// Diagnostic hook (tools/gp_profile.py): C[M,N] -= A[M,K] * B[K,N], all row-major, through the same fp64 tensor-core
+// GEMM the Cholesky / TRSM trailing updates use.
+int nib_gp_dgemm_sub(const double* d_A, const double* d_B, double* d_C, int M, int N, int K, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_A && d_B && d_C && M > 0 && N > 0 && K > 0, "nib_gp_dgemm_sub: bad arguments");
+  DgemmArgs g;
+  g.A = d_A; g.sai = K; g.sat = 1;
+  g.B = d_B; g.sbt = N; g.sbj = 1;
+  g.C = d_C; g.ldc = N;
+  g.M = M; g.N = N; g.K = K; g.lower_only = 0;
+  return dgemm_sub(g, (cudaStream_t)stream);
 }
 
 int nib_gp_trsm(const double* d_L, int n, int ldl, double* d_B, int nrhs, int ldb, int trans, void* stream) {
