@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = "masked forward evals/sec (ResNet-101 224^2)"
 UNIT = "evals/s"
 FLOPS_PER_EVAL = 15.602810880e9  # SURVEY.md §8d, conv+fc 2*MAC, torchvision 0.26 resnet101
+ACT_BYTES_PER_EVAL = (15.78e6 + 16.23e6) * 2  # conv input + output elements per eval, bf16
 
 
 def parse_args():
@@ -49,10 +50,25 @@ def parse_args():
     ap.add_argument("--arch", default="resnet101")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gp", action="store_true")
-    ap.add_argument("--gp-n", type=int, default=4096)
+    ap.add_argument("--gp-n", type=int, default=8192, help="GP training-set size (BASELINE configs[3]: n = 8192)")
     ap.add_argument("--graph", action="store_true", help="replay each micro-batch forward as a CUDA graph")
     ap.add_argument("--profile-json", default=None, help="write the per-op CUDA-event profile of one micro-batch here")
     return ap.parse_args()
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tcgen05 conv launches of ONE micro-batch-256 forward, from the
+    committed ncu capture (profiles/, one pass with cache control on: cold-L2 per launch), averaged per launch."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_ncu_all_launches_one_forward_v3_mb256.csv")
+    if not os.path.exists(p):
+        return None, None
+    tot, n = 0.0, 0
+    for r in csv.DictReader(open(p)):
+        if r["kernel"].startswith("conv_tc"):
+            tot += float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])
+            n += 1
+    return (tot / n if n else None), n
 
 
 def load_peaks():
@@ -307,9 +323,16 @@ def run_ours(args):
         n_tc = sum(1 for p in prof if p[1] == 1)
         if n_tc and tc_ms > 0:
             ach = tc_fl / (tc_ms / 1e3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": ach,
+            traffic, n_cap = ncu_traffic_per_launch()
+            if traffic is not None and min(mb, per) != 256:
+                traffic = traffic * min(mb, per) / 256.0    # the capture was taken at micro-batch 256
+            roofline = {"bound": "tensor", "kernel": "conv_tc3_kernel (tcgen05 cta_group::2 implicit GEMM)", "achieved": ach,
                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                        "traffic_source": "profiles/r01_ncu_all_launches_one_forward_v3_mb256.csv: mean DRAM bytes per conv "
+                                          "launch (ncu, cold L2 per launch), scaled to this micro-batch",
+                        "algorithmic_bytes_per_launch": ACT_BYTES_PER_EVAL * min(mb, per) / n_tc,
+                        "flops_per_launch": tc_fl / n_tc,
                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                         "launches_per_forward": n_tc, "share_of_forward": tc_ms / all_ms if all_ms else None,
                         "per_kind_ms": {"simt_conv": sum(p[0] for p in prof if p[1] == 0), "tc_conv": tc_ms,
@@ -376,9 +399,14 @@ def gp_bench(nib, torch, np, n, S):
     fit_ms, pred_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
     chol_flops = n ** 3 / 3
     trsm_flops = float(n) * n * n
+    fp64_peak = 37.1   # mma.sync.m8n8k4.f64 chains measured on this pool's B200 (tools/microbench/fp64_peak.cu)
     return {"n": n, "m": n, "fit_ms": fit_ms, "predict_ei_ms": pred_ms, "fit_plus_predict_ms": fit_ms + pred_ms,
             "fp64_tflops_fit": chol_flops / (fit_ms / 1e3) / 1e12, "fp64_tflops_predict": trsm_flops / (pred_ms / 1e3) / 1e12,
-            "note": "fixed theta (optimizer=None); includes host upload of masks and y"}
+            "roofline": {"bound": "fp64 tensor pipe (DMMA)", "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac_fit": chol_flops / (fit_ms / 1e3) / 1e12 / fp64_peak,
+                         "frac_predict": trsm_flops / (pred_ms / 1e3) / 1e12 / fp64_peak,
+                         "peak_source": "tools/microbench/fp64_peak.cu on B200: DFMA 34.1, DMMA 37.1 TFLOP/s"},
+            "note": "fixed theta (optimizer=None); n^3/3 (Cholesky) and m*n^2 (variance TRSM) flops; includes host upload of masks and y"}
 
 
 def main():
