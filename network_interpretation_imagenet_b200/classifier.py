@@ -32,7 +32,7 @@ def _f32(t: torch.Tensor) -> np.ndarray:
 def fold_bn(conv_w: torch.Tensor, conv_b: torch.Tensor | None, bn: nn.BatchNorm2d | None):
     """conv -> BN(eval) == conv with w*scale, b' = beta + (b - mean)*scale,  scale = gamma/sqrt(var+eps)."""
     w = conv_w.detach().double()
-    b = conv_b.detach().double() if conv_b is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    b = conv_b.detach().double() if conv_b is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
     if bn is not None:
         scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
         w = w * scale.view(-1, 1, 1, 1)
