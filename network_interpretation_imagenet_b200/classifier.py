@@ -235,7 +235,10 @@ def _lower_tv_resnet(m, hw, prec, precision, max_batch):
     stem_tc = (precision == "bf16" and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3) and cin <= 8)
     # tcgen05 stem: 8-channel-padded pixels (16 B) inside a 3-pixel zero halo, so each filter row of an output pixel
     # is one contiguous 128 B window (conv_tc.cu tc_conv_is_stem)
-    x_in = b.buffer(H, W, 8, pad=3, pooled=False) if stem_tc else b.buffer(H, W, _in_cpad(cin), pooled=False)
+    # 4-channel pixels (8 B) inside a 3-pixel zero halo when the image has <= 3 channels: the stem's TMA box then covers
+    # two filter rows per K block (conv_tc.cu tc_conv_is_stem4); 8-channel pixels otherwise
+    x_in = (b.buffer(H, W, 4 if cin <= 4 else 8, pad=3, pooled=False) if stem_tc
+            else b.buffer(H, W, _in_cpad(cin), pooled=False))
     Hc, Wc = _out_hw(H, c1.kernel_size[0], c1.stride[0], c1.padding[0]), _out_hw(W, c1.kernel_size[0], c1.stride[0], c1.padding[0])
     t = b.buffer(Hc, Wc, c1.out_channels)
     w, bias = fold_bn(c1.weight, c1.bias, m.bn1)
@@ -386,7 +389,7 @@ def _lower_tv_densenet(m, hw, prec, precision, max_batch):
     b = _Builder(prec, max_batch)
     c0 = f.conv0
     stem_tc = (precision == "bf16" and c0.kernel_size == (7, 7) and c0.stride == (2, 2) and c0.padding == (3, 3))
-    x_in = b.buffer(H, W, 8, pad=3, pooled=False) if stem_tc else b.buffer(H, W, _in_cpad(3), pooled=False)
+    x_in = b.buffer(H, W, 4, pad=3, pooled=False) if stem_tc else b.buffer(H, W, _in_cpad(3), pooled=False)
     Hc, Wc = _out_hw(H, 7, 2, 3), _out_hw(W, 7, 2, 3)
     t = b.buffer(Hc, Wc, c0.out_channels)
     w, bias = fold_bn(c0.weight, None, f.norm0)

@@ -45,7 +45,8 @@ struct TcKernelParams {
   int num_k_blocks;
   int cblocks;      // Cin / 64
   int S;            // filter width (tap -> (r, s))
-  int im2col;       // 0: tiled 2D A map, 1: im2col 4D A map, 2: stem rows (overlapping-window 4D tiled map)
+  int im2col;       // 0: tiled 2D A map, 1: im2col 4D A map, 2: stem rows (overlapping-window 4D tiled map, 8-channel
+                    // pixels, one filter row per K block), 3: stem row PAIRS (5D map, 4-channel pixels, v3 only)
   int tile_rows;    // valid output rows per M tile (128; Q for the stem mode: one output row per tile)
   int a_bytes;      // bytes the A load delivers per stage (tile_rows * 128)
   int P, Q, stride, pad;
@@ -176,6 +177,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;  // SBO
   d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+// K-major, 64B-swizzled smem tile: rows of 64 B (32 bf16 of K), 8-row groups 512 B apart (cute LayoutType SWIZZLE_64B = 4)
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 
@@ -786,6 +798,13 @@ __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1,
+                                             int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c,
                                                     int w, int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -979,8 +998,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (elect_one()) {
         const uint32_t lb = mapa_shared(bres_full_bar, 0);
         if (rank == 0) mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(2 * p.num_k_blocks * SM::BH_BYTES));
-        for (int kb = 0; kb < p.num_k_blocks; ++kb)
-          tma2_load_2d(smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES, &tmB, lb, kb * TC_BLOCK_K, b_row0);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const uint32_t dst = smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES;
+          if (p.im2col == 3) {   // 64B-swizzled: the K block is two 32-element atoms
+            tma2_load_2d(dst, &tmB, lb, kb * TC_BLOCK_K, b_row0);
+            tma2_load_2d(dst + SM::BH_BYTES / 2, &tmB, lb, kb * TC_BLOCK_K + 32, b_row0);
+          } else {
+            tma2_load_2d(dst, &tmB, lb, kb * TC_BLOCK_K, b_row0);
+          }
+        }
       }
       __syncwarp();
     }
@@ -997,7 +1023,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int pp = rem / p.Q, qq = rem - pp * p.Q;
         w0 = qq * p.stride - p.pad;
         h0 = pp * p.stride - p.pad;
-      } else if (p.im2col == 2) {
+      } else if (p.im2col >= 2) {
         img = m_tile / p.P;
         h0 = (m_tile - img * p.P) * p.stride;
       }
@@ -1017,6 +1043,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma2_load_im2col_4d(a_dst, &tmA, lbar, c0, w0, h0, img, (uint16_t)tap_s, (uint16_t)tap_r);
           } else if (p.im2col == 2) {
             tma2_load_4d(a_dst, &tmA, lbar, 0, 0, h0 + kb, img);
+          } else if (p.im2col == 3) {
+            // K block kb = filter rows 2kb, 2kb+1: two 64B-swizzled K atoms of [Q rows x 32 elements]
+            tma2_load_4d(a_dst, &tmA, lbar, 0, 0, h0 + 2 * kb, img);
+            tma2_load_4d(a_dst + SM::A_BYTES / 2, &tmA, lbar, 0, 0, h0 + 2 * kb + 1, img);
           } else {
             tma2_load_2d(a_dst, &tmA, lbar, c0, m0);
           }
@@ -1063,12 +1093,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
-            const uint64_t adesc = make_smem_desc_sw128(a_addr);
-            const uint64_t bdesc = make_smem_desc_sw128(BRES ? smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES
-                                                             : a_addr + SM::A_BYTES);
+            const uint32_t b_addr = BRES ? smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES : a_addr + SM::A_BYTES;
+            if (BRES && p.im2col == 3) {
+              // 64B-swizzled operands: K atom a (32 elements) at +a * half the tile, 16-element step inside it = +32 B
 #pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-              umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+              for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                const uint64_t adesc = make_smem_desc_sw64(a_addr + (k >> 1) * (SM::A_BYTES / 2) + (k & 1) * 32);
+                const uint64_t bdesc = make_smem_desc_sw64(b_addr + (k >> 1) * (SM::BH_BYTES / 2) + (k & 1) * 32);
+                umma2_bf16(d_tmem, adesc, bdesc, idesc, (kk | k) != 0);
+              }
+            } else {
+              const uint64_t adesc = make_smem_desc_sw128(a_addr);
+              const uint64_t bdesc = make_smem_desc_sw128(b_addr);
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+                umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+            }
             umma2_commit_both(empty_bar(stage));
             if (kk == p.num_k_blocks - 1) umma2_commit_both(tmem_full_bar(ab));
           }
@@ -1311,8 +1351,22 @@ bool tc_conv_is_stem(const ConvParams& p) {
          (p.Win + 2 * p.in_halo) >= 2 * (p.Q - 1) + 8;
 }
 
+// Same stem on 4-channel-padded pixels (8 B): a K block is TWO filter rows x (7 taps + 1 filler) x 4 channels.  Each
+// filter row is its own 64B-swizzled K atom [Q pixels x 32 elements] (a 64 B inner box under the 128 B swizzle gets
+// padded to 128 B rows by the copy engine, measured with tools/stem_diag.py, hence SWIZZLE_64B + matching UMMA
+// descriptors).  K = 4 x 64 instead of 7 x 64: 43 % fewer activation bytes through the TMA and 43 % fewer MMAs.
+// CTA-pair kernel with resident weights only.
+static int tc_version();
+bool tc_conv_is_stem4(const ConvParams& p) {
+  return tc_version() >= 3 && p.R == 7 && p.S == 7 && p.stride == 2 && p.pad == 3 && p.Cin <= 4 && p.in_cstride == 4 &&
+         p.in_coff == 0 && p.in_halo == 3 && p.Cout % 64 == 0 && p.Q <= TC_BLOCK_M && p.out_halo == 0 &&
+         p.out_cstride % 8 == 0 && p.out_coff % 8 == 0 && p.pre_scale == nullptr && p.res == nullptr &&
+         p.w_alt != nullptr && (p.Win + 2 * p.in_halo) % 2 == 0 && (p.Win + 2 * p.in_halo) >= 2 * (p.Q - 1) + 8 &&
+         (p.Hin + 2 * p.in_halo) >= 2 * (p.P - 1) + 8;
+}
+
 bool tc_conv_supported(const ConvParams& p) {
-  if (tc_conv_is_stem(p)) return true;
+  if (tc_conv_is_stem(p) || tc_conv_is_stem4(p)) return true;
   if (p.Cin % TC_BLOCK_K != 0) return false;
   if (p.in_cstride % 8 != 0 || p.in_coff % 8 != 0) return false;   // 16 B TMA alignment
   if (p.Cout % 32 != 0) return false;
@@ -1402,6 +1456,48 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
   plan->err_flag = g_err_flag;
   plan->block_n = pick_block_n(p.Cout, p.res != nullptr, p.R);
   plan->tile_rows = TC_BLOCK_M;
+  if (tc_conv_is_stem4(p)) {
+    plan->im2col = 3;
+    plan->cblocks = 1;
+    plan->num_k_blocks = 4;
+    plan->tile_rows = p.Q;
+    const int Hp = p.Hin + 6, Wp = p.Win + 6;
+    {
+      // one filter row of one output row: {window element (8 pixels x 4 ch), output pixel q (+2 pixels), input row, image}
+      cuuint64_t dims[4] = {32, (cuuint64_t)p.Q, (cuuint64_t)Hp, (cuuint64_t)max_batch};
+      cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
+      cuuint32_t box[4] = {32, (cuuint32_t)p.Q, 1, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = g_encodeTiled(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides,
+                                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (stem, 4-channel rows, 64B swizzle) failed (%d)", (int)r);
+        delete plan;
+        return NIB_ECUDA;
+      }
+    }
+    rc = finish_plan(plan, p, max_batch, p.w_alt, 4 * 64);
+    if (rc != NIB_OK) { delete plan; return rc; }
+    {
+      // weights [Cout][256] as 64B-swizzled K atoms of 32 elements, BLOCK_N/2 rows per CTA (overrides finish_plan's map)
+      cuuint64_t dims[2] = {256, (cuuint64_t)p.Cout};
+      cuuint64_t strides[1] = {256 * 2};
+      cuuint32_t box[2] = {32, (cuuint32_t)(plan->block_n / 2)};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = g_encodeTiled(&plan->tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.w_alt), dims, strides,
+                                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (stem weights, 64B swizzle) failed (%d)", (int)r);
+        delete plan;
+        return NIB_ECUDA;
+      }
+    }
+    plan->tmB = plan->tmBh;
+    *out = plan;
+    return NIB_OK;
+  }
   if (tc_conv_is_stem(p)) {
     plan->im2col = 2;
     plan->cblocks = 1;

@@ -185,6 +185,18 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
     NIB_CUDA(cudaMalloc(&op.d_w, nel * 4 + 256));
     NIB_CUDA(cudaMemcpy(op.d_w, krsc.data(), nel * 4, cudaMemcpyHostToDevice));
   }
+  if (net->bf16 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Cin <= 4 && bi.C == 4 && bi.pad == 3) {
+    // 4-channel pixels: K block kb = filter rows (2kb, 2kb+1), each (7 taps + 1 filler) x 4 channels; row 7 is zero
+    std::vector<uint16_t> hb((size_t)d->Cout * 4 * 64, 0);
+    for (int co = 0; co < d->Cout; ++co)
+      for (int r = 0; r < 7; ++r)
+        for (int s = 0; s < 7; ++s)
+          for (int c = 0; c < d->Cin; ++c)
+            hb[((size_t)co * 8 + r) * 32 + s * 4 + c] =
+                f32_to_bf16_rn(h_weight[(((size_t)co * d->Cin + c) * 7 + r) * 7 + s]);
+    NIB_CUDA(cudaMalloc(&op.d_w_alt, hb.size() * 2 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w_alt, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  }
   if (net->bf16 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Cin <= 8 && bi.C == 8 && bi.pad == 3) {
     std::vector<uint16_t> hb((size_t)d->Cout * 7 * 64, 0);
     for (int co = 0; co < d->Cout; ++co)

@@ -123,8 +123,9 @@ def test_conv_simt_vs_torch(nib, precision, case):
     assert err <= (1e-5 if precision == "fp32" else 1.2e-2) * scale
 
 
+@pytest.mark.parametrize("cpix", [8, 4])
 @pytest.mark.parametrize("H", [224, 64, 50])
-def test_stem_7x7_tcgen05_vs_torch(nib, H):
+def test_stem_7x7_tcgen05_vs_torch(nib, H, cpix):
     """torchvision conv1 (7x7/2, pad 3, Cin=3) through the overlapping-window TMA map: one output row per tile."""
     from network_interpretation_imagenet_b200 import _lib
     from network_interpretation_imagenet_b200.classifier import _Builder, Classifier, _out_hw
@@ -134,7 +135,7 @@ def test_stem_7x7_tcgen05_vs_torch(nib, H):
     bias = torch.randn(Cout, generator=g) * 0.1
     x = torch.randn(N, 3, H, H, generator=g)
     b = _Builder(_lib.PREC_BF16, N)
-    x_in = b.buffer(H, H, 8, pad=3, pooled=False)
+    x_in = b.buffer(H, H, cpix, pad=3, pooled=False)   # 8-channel pixels: one filter row per K block; 4: row pairs
     Ho = _out_hw(H, 7, 2, 3)
     out = b.buffer(Ho, Ho, Cout, pooled=False)
     b.conv(x_in, 3, out, Cout, w, bias, 7, 2, 3, relu=True)
