@@ -128,6 +128,8 @@ class Classifier:
         _lib.check(self.lib.nib_net_buffer_info(self.h, in_buf, C.byref(ptr), C.byref(H), C.byref(W), C.byref(Cc),
                                                 C.byref(pad), C.byref(dt)), "nib_net_buffer_info")
         self.in_c_stride, self.in_pad = Cc.value, pad.value
+        self._replicas: list["Classifier"] = []     # extra copies (own activation buffers) driven from side streams
+        self._streams: list = []
 
     def __del__(self):
         try:
@@ -139,7 +141,21 @@ class Classifier:
 
     # -- construction --------------------------------------------------------------------------
     @staticmethod
-    def from_torch(module: nn.Module, input_hw=None, precision: str = "bf16", max_batch: int = 128) -> "Classifier":
+    def from_torch(module: nn.Module, input_hw=None, precision: str = "bf16", max_batch: int = 128,
+                   streams: int = 1) -> "Classifier":
+        """streams > 1: that many copies of the lowered network (weights + activation buffers each), fed round-robin with
+        consecutive micro-batches from their own CUDA streams by `forward` / `forward_masked`.  Every conv layer is a
+        persistent kernel that fills the GPU, so copies do not run side by side; what overlaps is one kernel's ramp-up
+        with the previous kernel's partial last wave and drain (measured +5 % on ResNet-101, tools/overlap_exp.py)."""
+        c = Classifier._from_torch_one(module, input_hw, precision, max_batch)
+        for _ in range(max(1, int(streams)) - 1):
+            c._replicas.append(Classifier._from_torch_one(module, input_hw, precision, max_batch))
+        if c._replicas:
+            c._streams = [torch.cuda.Stream() for _ in range(len(c._replicas) + 1)]
+        return c
+
+    @staticmethod
+    def _from_torch_one(module: nn.Module, input_hw, precision: str, max_batch: int) -> "Classifier":
         prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
         m = module.module if isinstance(module, nn.DataParallel) else module  # cifar :75 wraps in DataParallel
         if hasattr(m, "layer4") and hasattr(m, "fc") and hasattr(m, "maxpool"):
@@ -160,11 +176,34 @@ class Classifier:
 
     def set_graph(self, enable: bool):
         _lib.check(self.lib.nib_net_set_graph(self.h, int(enable)), "nib_net_set_graph")
+        for r in self._replicas:
+            r.set_graph(enable)
 
     def launch_counts(self):
+        """(all kernel launches, tcgen05 launches) so far, summed over the stream copies."""
         a, b = C.c_longlong(), C.c_longlong()
         _lib.check(self.lib.nib_net_launch_counts(self.h, C.byref(a), C.byref(b)), "nib_net_launch_counts")
-        return a.value, b.value
+        ra = [r.launch_counts() for r in self._replicas]
+        return a.value + sum(x[0] for x in ra), b.value + sum(x[1] for x in ra)
+
+    def _round_robin(self, N: int, launch):
+        """launch(copy, i, n) for every micro-batch [i, i+n); with stream copies, micro-batch j goes to copy j % K on its
+        own stream, fenced against the caller's stream on both sides (inputs are ready, outputs are visible)."""
+        if not self._replicas:
+            for i in range(0, N, self.max_batch):
+                launch(self, i, min(self.max_batch, N - i))
+            return
+        main = torch.cuda.current_stream()
+        copies = [self] + self._replicas
+        used = min(len(copies), (N + self.max_batch - 1) // self.max_batch)
+        for s in self._streams[:used]:
+            s.wait_stream(main)
+        for j, i in enumerate(range(0, N, self.max_batch)):
+            k = j % len(copies)
+            with torch.cuda.stream(self._streams[k]):
+                launch(copies[k], i, min(self.max_batch, N - i))
+        for s in self._streams[:used]:
+            main.wait_stream(s)
 
     def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """x: [N,C,H,W] fp32 CUDA (the tensor the reference feeds `model(...)`).  Any N; chunks of max_batch."""
@@ -176,11 +215,12 @@ class Classifier:
             raise ValueError(f"input {tuple(x.shape)} does not match network input {(self.C, self.H, self.W)}")
         if out is None:
             out = torch.empty(N, self.num_classes, dtype=torch.float32, device=x.device)
-        st = _lib.stream_handle()
-        for i in range(0, N, self.max_batch):
-            n = min(self.max_batch, N - i)
-            _lib.check(self.lib.nib_net_forward(self.h, x[i:i + n].data_ptr(), _lib.IN_NCHW_F32, n,
-                                                out[i:i + n].data_ptr(), st), "nib_net_forward")
+
+        def launch(c, i, n):
+            _lib.check(c.lib.nib_net_forward(c.h, x[i:i + n].data_ptr(), _lib.IN_NCHW_F32, n,
+                                             out[i:i + n].data_ptr(), _lib.stream_handle()), "nib_net_forward")
+
+        self._round_robin(N, launch)
         return out
 
     def forward_masked(self, synth, sel_bits, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -190,12 +230,13 @@ class Classifier:
         N = int(d_sel.shape[0])
         if out is None:
             out = torch.empty(N, self.num_classes, dtype=torch.float32, device=d_sel.device)
-        st = _lib.stream_handle()
-        for i in range(0, N, self.max_batch):
-            n = min(self.max_batch, N - i)
+
+        def launch(c, i, n):
             a = synth.mask_args(d_sel[i:i + n], mode, None, 0, 0)
-            _lib.check(self.lib.nib_net_forward_masked(self.h, C.byref(a), out[i:i + n].data_ptr(), st),
+            _lib.check(c.lib.nib_net_forward_masked(c.h, C.byref(a), out[i:i + n].data_ptr(), _lib.stream_handle()),
                        "nib_net_forward_masked")
+
+        self._round_robin(N, launch)
         return out
 
     def profile(self, N: int):

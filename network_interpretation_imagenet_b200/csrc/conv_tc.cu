@@ -59,6 +59,8 @@ struct TcKernelParams {
   // v3 L2 prefetch by the (mostly idle) epilogue warps: the activation rows / residual rows of the tile this CTA will
   // work on two tiles from now, so the producer's TMA loads hit L2 instead of paying the DRAM round trip with a ring
   // that holds well under one tile.  1x1 stride-1 layers only (rows are contiguous channel vectors).
+  int m_rev;                 // v3: walk the M tiles from the last to the first (serpentine order across layers: a layer that
+                             // starts where its producer finished finds the most recently written rows still in L2)
   int k_rot;                 // v3: CTA pair i starts its K loop at block (i * k_rot) % num_k_blocks (0: everyone at block 0)
   const char* pf_a;          // first byte of the activation matrix slice (row 0, channel in_coff); null: off
   long long pf_a_pitch;      // bytes between rows
@@ -1012,7 +1014,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+      const int mp = tile / p.n_tiles;
+      const int m_tile = (p.m_rev ? m_pairs - 1 - mp : mp) * 2 + (int)rank;
       const int m0 = m_tile * p.tile_rows;
       const int n0 = n_tile * BLOCK_N;
       int w0 = 0, h0 = 0, img = 0;
@@ -1152,7 +1155,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto prefetch_tile = [&](int ft) {
       if (ft >= total_tiles) return;
       const int fn = ft % p.n_tiles;
-      const int fm0 = ((ft / p.n_tiles) * 2 + (int)rank) * TC_BLOCK_M;
+      const int fmp = ft / p.n_tiles;
+      const int fm0 = ((p.m_rev ? m_pairs - 1 - fmp : fmp) * 2 + (int)rank) * TC_BLOCK_M;
       if (p.pf_a != nullptr) {
         // the n-tiles that share these activation rows run on other CTA pairs at the same time: split the rows
         const int rows_per = p.n_tiles <= TC_BLOCK_M ? TC_BLOCK_M / p.n_tiles : 1;
@@ -1178,7 +1182,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (dbg_on) t_loop0 = clock64();
     for (; tile < total_tiles; tile += step, it += (SM::SPLIT_COLS ? 1 : 2), ++lt) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+      const int mp = tile / p.n_tiles;
+      const int m_tile = (p.m_rev ? m_pairs - 1 - mp : mp) * 2 + (int)rank;
       const int m0 = m_tile * p.tile_rows;
       const int n0 = n_tile * BLOCK_N;
       const int ab = it & 1;
@@ -1610,7 +1615,8 @@ static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStre
     attr_set = true;
   }
   const int pair_tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
-  const int max_pairs = num_sms() / 2;
+  static const int pair_cap = [] { const char* e = getenv("NIB_TC_PAIRS"); return e ? atoi(e) : 0; }();   // experiment: leave SMs to a second stream
+  const int max_pairs = pair_cap > 0 && pair_cap < num_sms() / 2 ? pair_cap : num_sms() / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
   // launched with programmatic stream serialization: the CTAs become resident (and run their prologue) as the SMs of
   // the previous kernel free up, then block in griddepcontrol.wait until that kernel has completed
@@ -1755,6 +1761,14 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
     static int krot = -1;
     if (krot < 0) { const char* e = getenv("NIB_TC_KROT"); krot = e ? atoi(e) : 0; }   // measured: no gain from de-synchronising the pairs; default keeps one K order
     kp.k_rot = krot;
+  }
+  {
+    // serpentine M order: the 1x1 reductions (Cin > Cout) read the tensor the previous expansion just wrote, and the
+    // expansion's residual is the tensor the reduction just read; walking the reductions backwards makes each layer start
+    // on the rows its predecessor touched last
+    static int serp = -1;
+    if (serp < 0) { const char* e = getenv("NIB_TC_SERP"); serp = e ? atoi(e) : 0; }
+    kp.m_rev = (serp && plan->v3 && p.R == 1 && p.stride == 1 && p.Cin > p.Cout) ? 1 : 0;
   }
   static const bool no_pf = getenv("NIB_TC_L2PF") == nullptr;   // measured: no gain (profiles/README.md); opt-in
   if (plan->v3 && !no_pf && plan->tile_rows == TC_BLOCK_M) {

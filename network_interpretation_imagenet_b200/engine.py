@@ -47,7 +47,7 @@ class PerturbationEngine:
 
     def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
                  max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False,
-                 refine_ties: float | None = None):
+                 refine_ties: float | None = None, streams: int = 1):
         _lib.load()
         self.device = torch.device(device)
         self.target = int(target)
@@ -55,7 +55,7 @@ class PerturbationEngine:
         self.group = group
         self.synth = MaskSynth(image, segments, S=S, device=device)
         self.classifier = model if isinstance(model, Classifier) else Classifier.from_torch(
-            model, (self.synth.H, self.synth.W), precision=precision, max_batch=max_batch)
+            model, (self.synth.H, self.synth.W), precision=precision, max_batch=max_batch, streams=streams)
         self.refine_ties = refine_ties if self.classifier.precision == "bf16" else None
         self._model_src = None if isinstance(model, Classifier) else model
         self._fp32 = None

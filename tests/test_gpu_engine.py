@@ -66,6 +66,25 @@ def test_cifar_config_end_to_end_fp32(nib):
     np.testing.assert_allclose(out["target_prob"].cpu().numpy(), tprob, rtol=2e-4, atol=1e-6)
 
 
+def test_stream_copies_give_bit_identical_scores(nib):
+    """Classifier copies on side streams (micro-batches round-robin) must not change a single bit of the result."""
+    raw = synthetic.synthetic_image("cifar")
+    seg = synthetic.voronoi_labels(32, 32, 20, seed=11)
+    model = ocls.load_resnet56()
+    sels = nib.draw_selections("cifar", 20, 200, seed=3)     # 200 masks, micro-batch 32: ragged last micro-batch
+    bits = nib.selection_bits(sels, 20)
+    d_org, _ = nib.prep_minmax_u8(raw)
+    outs = []
+    for streams in (1, 3):
+        eng = nib.PerturbationEngine(model, d_org, seg, 0, mode=nib.REMOVE_MINMAX, precision="bf16", max_batch=32, S=20,
+                                     streams=streams)
+        o = eng.score_masks(bits)
+        outs.append((o["target_prob"].cpu().numpy(), o["top1"].cpu().numpy()))
+        if streams == 3:
+            assert len(eng.classifier._replicas) == 2
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_imagenet_config_end_to_end_bf16(nib):
     """ResNet-101 224^2, S=50 keep-mode masks: identical top-1 on every mask, logits within 1e-2 (bf16)."""
     x = synthetic.synthetic_image("imagenet")
