@@ -287,6 +287,18 @@ int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S,
                 const uint64_t* d_sel, int sel_words, const float* d_y, int N, float* d_heat,
                 void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Superpixel label map — HOST function, HOST pointers, no device needed.
+ * Replaces `felzenszwalb(img_as_float(img), scale=100, sigma=0.5, min_size=50)`
+ * (generate_gp_training_data_imagenet.py:183, generate_gp_training_data_mnist.py:187,
+ * generate_gp_training_data_cifar.py:293, bayesian_active_learning_imagenet.py:150,:263,:463):
+ * scikit-image's graph-based segmentation (Gaussian blur, 8-connected colour-distance edges,
+ * sorted-edge union-find with threshold scale/|C|, min_size clean-up), labels 0..S-1 numbered in
+ * raster order of first appearance.  h_image [H,W,C] float64 in [0,1]; h_labels [H,W] int32.
+ * ---------------------------------------------------------------------------------------- */
+int nib_felzenszwalb(const double* h_image, int H, int W, int C, double scale, double sigma,
+                     int min_size, int32_t* h_labels, int* num_segments);
+
 #ifdef __cplusplus
 }
 #endif

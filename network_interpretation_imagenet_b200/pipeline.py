@@ -10,23 +10,39 @@ import shutil
 import numpy as np
 import torch
 
-from . import synthetic
 from .engine import PerturbationEngine
 from .masks import KEEP_MUL, REMOVE_MINMAX, draw_selections, prep_minmax_u8, selection_bits
 
 
-def segment_image(img_u8_hwc: np.ndarray, min_size: int, S_fallback: int, seed: int = 7) -> np.ndarray:
-    """`felzenszwalb(img_as_float(img), scale=100, sigma=0.5, min_size=...)` (imagenet :183, cifar :293, mnist :187)
-    when scikit-image is installed; otherwise a seeded Voronoi label map with S_fallback segments (scikit-image is
-    absent from this image; superpixel segmentation is a once-per-image CPU pre-step outside the hot path)."""
-    try:
-        from skimage.segmentation import felzenszwalb
-        from skimage.util import img_as_float
-        return felzenszwalb(img_as_float(img_u8_hwc), scale=100, sigma=0.5, min_size=min_size)
-    except ImportError:
-        H, W = img_u8_hwc.shape[:2]
-        print(f"[nib] scikit-image not installed: using a seeded Voronoi label map with {S_fallback} superpixels")
-        return synthetic.voronoi_labels(H, W, S_fallback, seed=seed)
+def felzenszwalb(image: np.ndarray, scale: float = 1.0, sigma: float = 0.8, min_size: int = 20) -> np.ndarray:
+    """Drop-in for `skimage.segmentation.felzenszwalb(image, scale, sigma, min_size)` on a float image in [0,1]
+    (H x W or H x W x C): libnib's native restatement of scikit-image's algorithm (csrc/segment.cu).  int64 labels H x W,
+    contiguous 0..S-1 in raster order of first appearance."""
+    import ctypes as C
+
+    from . import _lib
+    img = np.ascontiguousarray(np.atleast_3d(np.asarray(image, dtype=np.float64)))
+    H, W, Cc = img.shape
+    labels = np.empty((H, W), dtype=np.int32)
+    S = C.c_int()
+    _lib.check(_lib.load().nib_felzenszwalb(img.ctypes.data, H, W, Cc, float(scale), float(sigma), int(min_size),
+                                            labels.ctypes.data, C.byref(S)), "nib_felzenszwalb")
+    return labels.astype(np.int64)
+
+
+def img_as_float(img_u8: np.ndarray) -> np.ndarray:
+    """`skimage.util.img_as_float` of a uint8 image: float64, multiplied by 1/255 (scikit-image scales unsigned input
+    with `np.multiply(image, 1. / imax_in)`, not a division)."""
+    if img_u8.dtype != np.uint8:
+        raise TypeError("img_as_float restated for uint8 input only (what the reference passes, imagenet :178,:183)")
+    return np.multiply(img_u8, 1.0 / 255.0, dtype=np.float64)
+
+
+def segment_image(img_u8_hwc: np.ndarray, min_size: int, S_fallback: int | None = None, seed: int = 7) -> np.ndarray:
+    """`felzenszwalb(img_as_float(img), scale=100, sigma=0.5, min_size=...)` (imagenet :183, cifar :293, mnist :187),
+    computed by the library's own implementation (scikit-image is not needed).  S_fallback/seed are accepted for
+    backwards compatibility and ignored."""
+    return felzenszwalb(img_as_float(np.asarray(img_u8_hwc)), scale=100, sigma=0.5, min_size=min_size)
 
 
 def reset_dir(path: str) -> None:
