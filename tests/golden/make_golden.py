@@ -12,6 +12,7 @@ Fixtures
   masks_cifar.npz      generate_gp_training_data_cifar.py     a1 prep, draw, mask, min-max renormalise
   masks_mnist.npz      generate_gp_training_data_mnist.py     a1 prep, dummy randint + draw, mask, renormalise
   resnet56.npz         models/resnet.py createModel + shipped checkpoint -> logits of a seeded batch
+  mnist_net.npz        generate_gp_training_data_mnist.py :72-105 class statements + shipped checkpoint -> 4-tuple
   ei.npz               BayesianOptimization.expected_improvement on fixed (mu, sigma)
   gp_sklearn.npz       scikit-learn 1.9.0 GaussianProcessRegressor as built at BayesianOptimization.py:154-159
 """
@@ -157,6 +158,25 @@ def make_resnet56():
     np.savez_compressed(os.path.join(OUT, "resnet56.npz"), x=x.numpy(), logits=y.numpy())
 
 
+def make_mnist_net():
+    """generate_gp_training_data_mnist.py cannot be imported (argparse + dataset download at import time, :44-69): its
+    `conv` helper and `Classification_Net` class statements (:72-105) are exec'd as they stand, the shipped checkpoint is
+    loaded the way the script does (:157-158, key 'model'), and the 4-tuple of a seeded batch is recorded."""
+    rel = "generate_gp_training_data_mnist.py"
+    code, span = _extract(rel, "def conv(", "return x0, x1, x2, pred0")
+    ns = _run(code, {"nn": torch.nn, "torch": torch})
+    model = ns["Classification_Net"]()
+    ck = torch.load(os.path.join(REF, "saved_checkpoints/mnist/checkpoint.pth.tar"), map_location="cpu", weights_only=False)
+    model.load_state_dict(ck["model"])
+    model.eval()
+    torch.manual_seed(0)
+    x = torch.rand(4, 1, 28, 28)
+    with torch.no_grad():
+        x0, x1, x2, pred0 = model(x)
+    np.savez_compressed(os.path.join(OUT, "mnist_net.npz"), x=x.numpy(), pred0=pred0.numpy(), x2=x2.numpy(),
+                        x0_mean=x0.mean((2, 3)).numpy(), x1_mean=x1.mean((2, 3)).numpy(), ref_lines=np.array(span))
+
+
 def make_ei():
     rel = "BayesianOptimization.py"
     code, span = _extract(rel, "def expected_improvement(", "return -1 * expected_improvement")
@@ -225,6 +245,7 @@ if __name__ == "__main__":
     make_masks_cifar()
     make_masks_mnist()
     make_resnet56()
+    make_mnist_net()
     make_ei()
     make_gp_sklearn()
     for f in sorted(os.listdir(OUT)):

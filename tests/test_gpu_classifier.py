@@ -206,6 +206,16 @@ def test_mnist_net_fp32_with_taps(nib):
         assert rel_err(tap, ref.numpy()) <= TOL_FP32, name
 
 
+def test_mnist_net_fp32_golden(nib, golden_dir):
+    """Against the output of the reference's own Classification_Net class (tests/golden/make_golden.py make_mnist_net)."""
+    g = np.load(os.path.join(golden_dir, "mnist_net.npz"))
+    net = nib.Classifier.from_torch(ocls.load_mnist_net(), (28, 28), precision="fp32", max_batch=4)
+    got = net.forward(torch.from_numpy(g["x"]).cuda()).cpu().numpy()
+    assert rel_err(got, g["pred0"]) <= TOL_FP32
+    assert rel_err(net.read_tap("x2", 4).cpu().numpy(), g["x2"]) <= TOL_FP32
+    assert np.array_equal(got.argmax(1), g["pred0"].argmax(1))
+
+
 def test_mnist_net_bf16(nib):
     m = ocls.load_mnist_net()
     x = torch.rand(64, 1, 28, 28, generator=torch.Generator().manual_seed(4))

@@ -68,6 +68,18 @@ def test_resnet56_restated_matches_reference_module(golden_dir):
     np.testing.assert_allclose(y[0], kat, atol=2e-3)
 
 
+def test_mnist_net_restated_matches_reference_class(golden_dir):
+    """mnist_net.npz = the reference's own Classification_Net statements (mnist :72-105) exec'd + the shipped checkpoint."""
+    g = _load(golden_dir, "mnist_net.npz")
+    m = ocls.load_mnist_net()
+    with torch.no_grad():
+        x0, x1, x2, p = m(torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(p.numpy(), g["pred0"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(x2.numpy(), g["x2"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(x0.mean((2, 3)).numpy(), g["x0_mean"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(x1.mean((2, 3)).numpy(), g["x1_mean"], rtol=1e-5, atol=1e-5)
+
+
 def test_mnist_checkpoint_loads_strict():
     m = ocls.load_mnist_net()
     x = torch.rand(2, 1, 28, 28, generator=torch.Generator().manual_seed(1))
