@@ -97,31 +97,39 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) 
                : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1)
+// GTM = 128: one block per SM (64 accumulator doubles per thread).  GTM = 64: two blocks per SM, so one block's K loop
+// overlaps the other's C read-modify-write — with one block per SM every tile paid ~25 us of exposed epilogue/prologue
+// (rate model t = a + b*K fitted to 8.2 / 17 / 25.7 TFLOP/s at K = 64 / 256 / 4096), because the blocks of a wave
+// finish together and all fetch their 128 KB of C at the same moment.
+template <int GTM>
+__global__ void __launch_bounds__(256, GTM == 64 ? 2 : 1)
 dgemm_sub_kernel(DgemmArgs g) {
+  constexpr int MT = GTM / 16;          // 8-row MMA tiles per warp (warp tile = GTM/2 x 32)
+  constexpr int AE = GTM * GK / 256;    // A elements per thread per chunk
+  constexpr int ASP = GTM + 4;          // A pitch: = 8 words mod 32 for both tile heights
   const int bi = blockIdx.y, bj = blockIdx.x;
-  if (g.lower_only && bj > bi) return;
-  __shared__ __align__(16) double As[GK][GS];
+  if (g.lower_only && bj * GT > bi * GTM + GTM - 1) return;
+  __shared__ __align__(16) double As[GK][ASP];
   __shared__ __align__(16) double Bs[GK][GS];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = warp >> 2, wn = warp & 3;          // warp tile: rows wm*64.., cols wn*32..
+  const int wm = warp >> 2, wn = warp & 3;          // warp tile: rows wm*GTM/2.., cols wn*32..
   const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates (groupID, threadID_in_group)
-  const int i0 = bi * GT, j0 = bj * GT;
-  double acc[8][4][2];
+  const int i0 = bi * GTM, j0 = bj * GT;
+  double acc[MT][4][2];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < MT; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  // loader mapping: 128 x 16 elements each for A and B per chunk, 8 per thread; the fastest-varying thread index runs
-  // along the unit-stride direction of the operand so a warp reads whole 128 B lines.
+  // loader mapping: GTM x 16 elements of A and 128 x 16 of B per chunk; the fastest-varying thread index runs along the
+  // unit-stride direction of the operand so a warp reads whole 128 B lines.
   const bool a_t_fast = (g.sat == 1);
   const bool b_j_fast = (g.sbj == 1);
-  double av[8], bv[8];
+  double av[AE], bv[8];
   auto a_pos = [&](int e, int& ii, int& tt) {
     const int idx = tid + e * 256;
-    if (a_t_fast) { tt = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GT - 1); tt = idx >> 7; }
+    if (a_t_fast) { tt = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GTM - 1); tt = idx / GTM; }
   };
   auto b_pos = [&](int e, int& jj, int& tt) {
     const int idx = tid + e * 256;
@@ -129,12 +137,16 @@ dgemm_sub_kernel(DgemmArgs g) {
   };
   auto load_chunk = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int ii, tt, jj, t2;
+    for (int e = 0; e < AE; ++e) {
+      int ii, tt;
       a_pos(e, ii, tt);
-      b_pos(e, jj, t2);
       const int gi = i0 + ii, gt = k0 + tt;
       av[e] = (gi < g.M && gt < g.K) ? g.A[gi * g.sai + gt * g.sat] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int jj, t2;
+      b_pos(e, jj, t2);
       const int gj = j0 + jj, gt2 = k0 + t2;
       bv[e] = (gj < g.N && gt2 < g.K) ? g.B[gt2 * g.sbt + gj * g.sbj] : 0.0;
     }
@@ -143,68 +155,301 @@ dgemm_sub_kernel(DgemmArgs g) {
   for (int k0 = 0; k0 < g.K; k0 += GK) {
     __syncthreads();   // everyone is done reading the previous chunk
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int ii, tt, jj, t2;
+    for (int e = 0; e < AE; ++e) {
+      int ii, tt;
       a_pos(e, ii, tt);
-      b_pos(e, jj, t2);
       As[tt][ii] = av[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int jj, t2;
+      b_pos(e, jj, t2);
       Bs[t2][jj] = bv[e];
     }
     __syncthreads();
     if (k0 + GK < g.K) load_chunk(k0 + GK);
 #pragma unroll
     for (int t = 0; t < GK; t += 4) {
-      double a[8], b[4];
+      double a[MT], b[4];
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) a[mt] = As[t + fk][wm * 64 + mt * 8 + fr];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = As[t + fk][wm * (GTM / 2) + mt * 8 + fr];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[t + fk][wn * 32 + nt * 8 + fr];
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
     }
   }
-  // C -= acc.  The loads are gathered into registers in batches of 16 before any store of the batch: written as one
-  // read-modify-write per element the compiler must assume every store may alias the next load and serialises 64
-  // L2 round trips per thread (that, not the arithmetic, was 70 % of the tile time of the first version).
+  // C -= acc.  Each thread owns column pairs (2fk, 2fk+1): one 16-byte access per pair, so the four lanes of a fragment
+  // row cover a whole 64 B (two full sectors) — 8-byte accesses wrote every sector in four partial pieces and the
+  // read-modify-write of C ran at ~1 TB/s.  Loads are gathered in batches before any store of the batch (a store may
+  // alias the next load as far as the compiler knows, which would serialise the L2 round trips).
+  const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
 #pragma unroll
-  for (int mb = 0; mb < 8; mb += 2) {
-    double cv[2][4][2];
+  for (int mb = 0; mb < MT; mb += 2) {
+    double2 cv[2][4];
 #pragma unroll
     for (int m2 = 0; m2 < 2; ++m2) {
-      const int i = i0 + wm * 64 + (mb + m2) * 8 + fr;
+      const int i = i0 + wm * (GTM / 2) + (mb + m2) * 8 + fr;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int j = j0 + wn * 32 + nt * 8 + 2 * fk + c;
-          const bool ok = i < g.M && j < g.N && !(g.lower_only && j > i);
-          cv[m2][nt][c] = ok ? g.C[i * g.ldc + j] : 0.0;
+      for (int nt = 0; nt < 4; ++nt) {
+        const int j = j0 + wn * 32 + nt * 8 + 2 * fk;
+        const bool ok0 = i < g.M && j < g.N && !(g.lower_only && j > i);
+        const bool ok1 = i < g.M && j + 1 < g.N && !(g.lower_only && j + 1 > i);
+        if (vec_ok && ok0 && ok1) cv[m2][nt] = *reinterpret_cast<const double2*>(g.C + i * g.ldc + j);
+        else {
+          cv[m2][nt].x = ok0 ? g.C[i * g.ldc + j] : 0.0;
+          cv[m2][nt].y = ok1 ? g.C[i * g.ldc + j + 1] : 0.0;
         }
+      }
     }
 #pragma unroll
     for (int m2 = 0; m2 < 2; ++m2) {
-      const int i = i0 + wm * 64 + (mb + m2) * 8 + fr;
+      const int i = i0 + wm * (GTM / 2) + (mb + m2) * 8 + fr;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int j = j0 + wn * 32 + nt * 8 + 2 * fk + c;
-          const bool ok = i < g.M && j < g.N && !(g.lower_only && j > i);
-          if (ok) g.C[i * g.ldc + j] = cv[m2][nt][c] - acc[mb + m2][nt][c];
+      for (int nt = 0; nt < 4; ++nt) {
+        const int j = j0 + wn * 32 + nt * 8 + 2 * fk;
+        const bool ok0 = i < g.M && j < g.N && !(g.lower_only && j > i);
+        const bool ok1 = i < g.M && j + 1 < g.N && !(g.lower_only && j + 1 > i);
+        const double2 o = make_double2(cv[m2][nt].x - acc[mb + m2][nt][0], cv[m2][nt].y - acc[mb + m2][nt][1]);
+        if (vec_ok && ok0 && ok1) *reinterpret_cast<double2*>(g.C + i * g.ldc + j) = o;
+        else {
+          if (ok0) g.C[i * g.ldc + j] = o.x;
+          if (ok1) g.C[i * g.ldc + j + 1] = o.y;
         }
+      }
     }
   }
 }
 
 static int dgemm_sub(const DgemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return NIB_OK;
-  dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, GT));
-  dgemm_sub_kernel<<<grid, 256, 0, st>>>(g);
+  static const int tile_m = [] { const char* e = getenv("NIB_GP_TILE_M"); return e && atoi(e) == 128 ? 128 : 64; }();
+  dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, tile_m));
+  if (tile_m == 128) dgemm_sub_kernel<128><<<grid, 256, 0, st>>>(g);
+  else dgemm_sub_kernel<64><<<grid, 256, 0, st>>>(g);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }
+
+// ---- inverses of the 64 x 64 diagonal blocks -----------------------------------------------------
+// Every latency-bound triangular step (panel solve below a diagonal block, diagonal solve of a TRSM step, single-vector
+// solves) becomes a 64-deep matrix product once inv(Lkk) is known, and the rest of the solve is GEMM.  A dependent fp64
+// operation costs ~48 cycles here (measured: 64 elimination steps of ~25 dependent operations took 41.6 us), so the
+// inverse is built by block doubling with all 256 threads instead of 64 independent forward substitutions (27 us):
+// 4 x 4 diagonal blocks directly, then inv([[A,0],[B,C]]) = [[Ai,0],[-Ci*B*Ai,Ci]] for block sizes 4, 8, 16, 32 —
+// about 80 dependent operations in total.  Ls: the factor block (identity padded), Xs: the inverse (zeros above the
+// diagonal), both 64 x 65 in shared memory; called by all 256 threads.
+__device__ __forceinline__ void trtri64_coop(const double (*Ls)[NB + 1], double (*Xs)[NB + 1]) {
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < NB * NB; idx += 256) Xs[idx >> 6][idx & 63] = 0.0;
+  __syncthreads();
+  if (tid < NB) {   // 4 x 4 diagonal blocks: thread = (block, column)
+    const int b0 = tid & ~3, c = tid & 3;
+    double x[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double sacc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int t = 0; t < r; ++t) sacc = fma(-Ls[b0 + r][b0 + t], x[t], sacc);
+      x[r] = (r >= c) ? sacc / Ls[b0 + r][b0 + r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Xs[b0 + r][b0 + c] = x[r];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int sz = 4; sz < NB; sz *= 2) {
+    const int per = sz * sz;                    // elements of one off-diagonal block
+    const int total = (NB / (2 * sz)) * per;    // 32 * sz
+    // T = B * Ai, parked where the result block will live
+    double tv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      tv[e] = 0.0;
+      if (idx < total) {
+        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
+        double a0 = 0.0, a1 = 0.0;
+        for (int t = j; t + 1 < sz; t += 2) {    // Ai is lower triangular: Ai[t][j] = 0 for t < j
+          a0 = fma(Ls[base + sz + i][base + t], Xs[base + t][base + j], a0);
+          a1 = fma(Ls[base + sz + i][base + t + 1], Xs[base + t + 1][base + j], a1);
+        }
+        if ((sz - j) & 1) a0 = fma(Ls[base + sz + i][base + sz - 1], Xs[base + sz - 1][base + j], a0);
+        tv[e] = a0 + a1;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      if (idx < total) {
+        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
+        Xs[base + sz + i][base + j] = tv[e];
+      }
+    }
+    __syncthreads();
+    // O = -Ci * T
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      tv[e] = 0.0;
+      if (idx < total) {
+        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
+        double a0 = 0.0, a1 = 0.0;
+        int t = 0;
+        for (; t + 1 <= i; t += 2) {             // Ci[i][t] = 0 for t > i
+          a0 = fma(Xs[base + sz + i][base + sz + t], Xs[base + sz + t][base + j], a0);
+          a1 = fma(Xs[base + sz + i][base + sz + t + 1], Xs[base + sz + t + 1][base + j], a1);
+        }
+        if (t <= i) a0 = fma(Xs[base + sz + i][base + sz + t], Xs[base + sz + t][base + j], a0);
+        tv[e] = -(a0 + a1);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      if (idx < total) {
+        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
+        Xs[base + sz + i][base + j] = tv[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static constexpr size_t TRTRI_SMEM = (size_t)2 * NB * (NB + 1) * sizeof(double);   // Ls + Xs, dynamic (66.5 KB)
+
+// all diagonal blocks of a finished factor at once (TRSM entry points are stateless: they rebuild the inverses)
+__global__ void __launch_bounds__(256)
+trtri64_batched_kernel(const double* __restrict__ Lm, int ldl, int n, double* __restrict__ dinv) {
+  extern __shared__ __align__(16) double tt_smem[];
+  double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tt_smem);
+  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tt_smem + NB * (NB + 1));
+  const int k0 = blockIdx.x * NB;
+  const int nb = min(NB, n - k0);
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+    const int i = idx >> 6, j = idx & 63;
+    Ls[i][j] = (i < nb && j <= i) ? Lm[(size_t)(k0 + i) * ldl + k0 + j] : ((i == j) ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  trtri64_coop(Ls, Xs);
+  double* out = dinv + (size_t)blockIdx.x * NB * NB;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) out[idx] = Xs[idx >> 6][idx & 63];
+}
+
+// out = P * Q on one 64 x 64 tile with a 64-deep product, in place on the matrix operand:
+//   mode 0  rows [k0, k0+nb) of M  <-  D * rows          (forward TRSM step; tile = 64 columns from 64 * blockIdx.x)
+//   mode 1  rows [k0, k0+nb) of M  <-  D^T * rows        (backward TRSM step)
+//   mode 2  M[r0 + rows, k0 : k0+nb)  <-  rows * D^T     (panel below a Cholesky diagonal block; tile = 64 rows)
+// D = inverse of the diagonal block.  256 threads, 4 x 4 outputs each; the in-place operand is staged whole before any
+// store.  66 KB of dynamic shared memory.
+static constexpr int AP = NB + 2;   // Q pitch: keeps 16-byte alignment for the paired loads
+__global__ void __launch_bounds__(256)
+apply_dinv_kernel(const double* __restrict__ D, double* __restrict__ Mx, long long ld, int k0, int nb, int r0, int count,
+                  int mode, const int* __restrict__ info) {
+  extern __shared__ __align__(16) double ap_smem[];
+  double (*Ps)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(ap_smem);
+  double (*Qs)[AP] = reinterpret_cast<double (*)[AP]>(ap_smem + NB * (NB + 1));   // 4160 doubles: 16-byte aligned
+  if (info != nullptr && *info != 0) return;
+  const int tid = threadIdx.x;
+  const int o0 = blockIdx.x * NB;                 // first column (modes 0/1) or first row offset (mode 2) of this tile
+  // both 64 x 64 operands are fetched into registers first (32 independent loads in flight per thread), then parked:
+  // a load -> store loop pays one DRAM/L2 round trip per iteration
+  double mv[16], dv[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int idx = tid + e * 256;
+    const int a = idx >> 6, b = idx & 63;          // b runs along the unit-stride direction of both sources
+    dv[e] = D[a * NB + b];
+    if (mode == 2) mv[e] = (o0 + a < count && b < nb) ? Mx[(size_t)(r0 + o0 + a) * ld + k0 + b] : 0.0;
+    else mv[e] = (a < nb && o0 + b < count) ? Mx[(size_t)(k0 + a) * ld + o0 + b] : 0.0;
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int idx = tid + e * 256;
+    const int a = idx >> 6, b = idx & 63;
+    if (mode == 2) {
+      Ps[a][b] = mv[e];          // P[i][t] = rows
+      Qs[b][a] = dv[e];          // Q[t][j] = D[j][t]
+    } else {
+      Qs[a][b] = mv[e];          // Q[t][j] = rows
+      if (mode == 0) Ps[a][b] = dv[e]; else Ps[b][a] = dv[e];   // P = D or D^T
+    }
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int t = 0; t < NB; ++t) {
+    double pv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) pv[a] = Ps[4 * ty + a][t];
+    const double2 q01 = *reinterpret_cast<const double2*>(&Qs[t][4 * tx]);
+    const double2 q23 = *reinterpret_cast<const double2*>(&Qs[t][4 * tx + 2]);
+    const double qv[4] = {q01.x, q01.y, q23.x, q23.y};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(pv[a], qv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = 4 * ty + a, j = 4 * tx + b;
+      if (mode == 2) {
+        if (o0 + i < count && j < nb) Mx[(size_t)(r0 + o0 + i) * ld + k0 + j] = acc[a][b];
+      } else {
+        if (i < nb && o0 + j < count) Mx[(size_t)(k0 + i) * ld + o0 + j] = acc[a][b];
+      }
+    }
+}
+static constexpr size_t AP_SMEM = (size_t)(NB * (NB + 1) + 2 + NB * AP) * sizeof(double);
+
+static int apply_dinv(const double* D, double* Mx, long long ld, int k0, int nb, int r0, int count, int mode,
+                      const int* info, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    NIB_CUDA(cudaFuncSetAttribute(apply_dinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM));
+    attr = true;
+  }
+  if (count <= 0 || nb <= 0) return NIB_OK;
+  apply_dinv_kernel<<<ceil_div(count, NB), 256, AP_SMEM, st>>>(D, Mx, ld, k0, nb, r0, count, mode, info);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+__global__ void potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restrict__ info, double* __restrict__ dinv);
+static int trtri_attrs() {
+  static bool done = false;
+  if (!done) {
+    NIB_CUDA(cudaFuncSetAttribute(trtri64_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    NIB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    done = true;
+  }
+  return NIB_OK;
+}
+
+// scratch for the diagonal-block inverses of the factor currently being built / solved with
+static double* g_dinv = nullptr;
+static size_t g_dinv_cap = 0;
+static int ensure_dinv(int n) {
+  const size_t need = (size_t)ceil_div(n, NB) * NB * NB;
+  if (g_dinv_cap < need) {
+    if (g_dinv) cudaFree(g_dinv);
+    g_dinv_cap = need < (size_t)256 * NB * NB ? (size_t)256 * NB * NB : need;
+    NIB_CUDA(cudaMalloc(&g_dinv, g_dinv_cap * sizeof(double)));
+  }
+  return NIB_OK;
+}
+static inline int split64(int w) { return ((w / 2 + NB - 1) / NB) * NB; }   // NB <= split < w for w > NB
 
 // ---- Cholesky --------------------------------------------------------------------------------
 // Factor the nb x nb (<= 64) diagonal block at (k0,k0).  The block lives in registers: thread (br, bc) of a 16 x 16
@@ -212,8 +457,11 @@ static int dgemm_sub(const DgemmArgs& g, cudaStream_t st) {
 // through a double-buffered 64-entry smem vector, so a step costs one __syncthreads and 16 predicated FMAs per thread
 // (right-looking, the update order of LAPACK dpotf2 that scipy.linalg.cholesky ends in, _gpr.py:352).
 __global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restrict__ info) {
+potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restrict__ info, double* __restrict__ dinv) {
   __shared__ double colbuf[2][NB];
+  extern __shared__ __align__(16) double pd_smem[];   // the factored block and its inverse (dinv != null), TRTRI_SMEM bytes
+  double (*Lsh)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(pd_smem);
+  double (*Xsh)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(pd_smem + NB * (NB + 1));
   const int tid = threadIdx.x;
   const int br = tid >> 4, bc = tid & 15;
   double r[4][4];
@@ -243,8 +491,11 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restric
       if (tid == 0 && *info == 0) *info = k0 + j + 1;
       return;
     }
-    const double rs = sqrt(d);
-    const double inv = 1.0 / rs;
+    // one reciprocal square root (Newton-refined) instead of a square root followed by a division: the pivot chain is
+    // 64 steps long and every dependent fp64 operation on it costs ~48 cycles
+    double inv = rsqrt(d);
+    inv = fma(inv * 0.5, fma(-d * inv, inv, 1.0), inv);   // one more Newton step: full double precision
+    const double rs = d * inv;
     double lr[4], lc[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -266,7 +517,12 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restric
     for (int b = 0; b < 4; ++b) {
       const int i = 4 * br + a, j = 4 * bc + b;
       if (i < nb && j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = r[a][b];
+      if (dinv != nullptr) Lsh[i][j] = (j <= i) ? r[a][b] : 0.0;   // identity padding beyond nb comes out of the elimination itself
     }
+  if (dinv == nullptr) return;
+  __syncthreads();
+  trtri64_coop(Lsh, Xsh);
+  for (int idx = tid; idx < NB * NB; idx += 256) dinv[idx] = Xsh[idx >> 6][idx & 63];
 }
 
 // rows below the diagonal block: solve X * Lkk^T = A[i, k0:k0+nb], one row per thread; four interleaved partial sums
@@ -394,17 +650,41 @@ __device__ __forceinline__ void trsv_diag_warp(const double (*Ls)[NB + 1], doubl
 
 __global__ void __launch_bounds__(256)
 trsv_step_kernel(const double* __restrict__ Lm, int ldl, double* __restrict__ b, double* __restrict__ x, int n, int k0,
-                 int nb, int trans) {
+                 int nb, int trans, const double* __restrict__ dinv) {
   __shared__ double Ls[NB][NB + 1];
   __shared__ double xs[NB];
+  __shared__ double bs[NB];
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int i = idx / NB, j = idx - i * NB;
-    Ls[i][j] = (i < nb && j <= i) ? Lm[(size_t)(k0 + i) * ldl + k0 + j] : ((i == j) ? 1.0 : 0.0);
+  if (dinv != nullptr) {
+    // diagonal system through the block inverse: a 64 x 64 product (4 threads per row, 16-deep chains) instead of 64
+    // dependent divide / broadcast steps in one warp (~20 us of the 23 us this kernel used to take)
+    const double* D = dinv + (size_t)(k0 / NB) * NB * NB;
+    double dv[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dv[e] = D[tid + e * 256];
+    if (tid < NB) bs[tid] = tid < nb ? b[k0 + tid] : 0.0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int idx = tid + e * 256, a = idx >> 6, c = idx & 63;
+      if (trans) Ls[c][a] = dv[e]; else Ls[a][c] = dv[e];     // Ls = D or D^T
+    }
+    __syncthreads();
+    const int row = tid >> 2, q = tid & 3;
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc = fma(Ls[row][q * 16 + t], bs[q * 16 + t], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) xs[row] = acc;
+  } else {
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int i = idx / NB, j = idx - i * NB;
+      Ls[i][j] = (i < nb && j <= i) ? Lm[(size_t)(k0 + i) * ldl + k0 + j] : ((i == j) ? 1.0 : 0.0);
+    }
+    if (tid < NB) xs[tid] = tid < nb ? b[k0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 32) trsv_diag_warp(Ls, xs, nb, trans != 0);
   }
-  if (tid < NB) xs[tid] = tid < nb ? b[k0 + tid] : 0.0;
-  __syncthreads();
-  if (tid < 32) trsv_diag_warp(Ls, xs, nb, trans != 0);
   __syncthreads();
   // the solved entries go to a separate vector: blocks of this launch that start late must still read the unsolved b
   if (blockIdx.x == 0 && tid < nb) x[k0 + tid] = xs[tid];
@@ -430,7 +710,7 @@ trsv_step_kernel(const double* __restrict__ Lm, int ldl, double* __restrict__ b,
 
 static double* g_trsv_x = nullptr;
 static size_t g_trsv_cap = 0;
-static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, cudaStream_t st) {
+static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, const double* dinv, cudaStream_t st) {
   if (g_trsv_cap < (size_t)n) {
     if (g_trsv_x) cudaFree(g_trsv_x);
     g_trsv_cap = (size_t)n < 16384 ? 16384 : (size_t)n;
@@ -444,7 +724,7 @@ static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, cuda
     const int work = trans ? ceil_div(k0, 256) : ceil_div(n - (k0 + nb), 8);
     int grid = work < 1 ? 1 : work;
     if (grid > 4 * num_sms()) grid = 4 * num_sms();
-    trsv_step_kernel<<<grid, 256, 0, st>>>(L, ldl, b, g_trsv_x, n, k0, nb, trans);
+    trsv_step_kernel<<<grid, 256, 0, st>>>(L, ldl, b, g_trsv_x, n, k0, nb, trans, dinv);
     NIB_LAUNCH_CHECK();
   }
   NIB_CUDA(cudaMemcpyAsync(b, g_trsv_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -456,10 +736,11 @@ static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, cuda
 // per super-block.  The trailing GEMM is read-modify-write on its output: at K = 64 it measured 8-9 TFLOP/s (the tile's
 // C round trip dominates), at K = 256 17 TFLOP/s, at large K 25.7 of the 37 TFLOP/s DMMA peak (tools/gp_profile.py).
 static constexpr int NBO = 256;
+static const int NBC = [] { const char* e = getenv("NIB_GP_NBC"); const int v = e ? atoi(e) : 256; return v >= 64 && v % 64 == 0 ? v : 256; }();   // Cholesky super-block width
 
-static int trsm_impl(const double* L, int n, int ldl, double* B, int nrhs, int ldb, int trans, cudaStream_t st) {
+static int trsm_impl_v1(const double* L, int n, int ldl, double* B, int nrhs, int ldb, int trans, cudaStream_t st) {
   if (n <= 0 || nrhs <= 0) return NIB_OK;
-  if (nrhs == 1 && ldb == 1) return trsv_impl(L, n, ldl, B, trans, st);
+  if (nrhs == 1 && ldb == 1) return trsv_impl(L, n, ldl, B, trans, nullptr, st);
   const int cb = ceil_div(nrhs, 128);
   DgemmArgs g;
   g.lower_only = 0;
@@ -525,6 +806,95 @@ static int trsm_impl(const double* L, int n, int ldl, double* B, int nrhs, int l
     }
   }
   return NIB_OK;
+}
+
+
+// Recursive TRSM on the block inverses: solve rows [r0, r0+nr) given everything before (forward) / after (backward) has
+// been eliminated.  A leaf is one 64-deep product with inv(Lkk); every off-diagonal elimination is a GEMM whose depth is
+// half the current range — half of all flops run at depth n/2, a quarter at n/4, ... (the DMMA GEMM measured
+// 8 / 17 / 25.7 TFLOP/s at depth 64 / 256 / 4096), against depth 64 and 256 in the two-level blocked version.
+static int trsm_rec(const double* L, int ldl, double* B, int nrhs, int ldb, int r0, int nr, int trans, const double* dinv,
+                    cudaStream_t st) {
+  if (nr <= NB)
+    return apply_dinv(dinv + (size_t)(r0 / NB) * NB * NB, B, ldb, r0, nr, 0, nrhs, trans ? 1 : 0, nullptr, st);
+  const int h = split64(nr);
+  DgemmArgs g;
+  g.lower_only = 0;
+  g.N = nrhs;
+  g.ldc = ldb;
+  g.sbt = ldb; g.sbj = 1;
+  int rc;
+  if (!trans) {
+    if ((rc = trsm_rec(L, ldl, B, nrhs, ldb, r0, h, trans, dinv, st)) != NIB_OK) return rc;
+    g.A = L + (size_t)(r0 + h) * ldl + r0; g.sai = ldl; g.sat = 1;      // L[r0+h+i][r0+t]
+    g.B = B + (size_t)r0 * ldb;
+    g.C = B + (size_t)(r0 + h) * ldb;
+    g.M = nr - h; g.K = h;
+    if ((rc = dgemm_sub(g, st)) != NIB_OK) return rc;
+    return trsm_rec(L, ldl, B, nrhs, ldb, r0 + h, nr - h, trans, dinv, st);
+  }
+  if ((rc = trsm_rec(L, ldl, B, nrhs, ldb, r0 + h, nr - h, trans, dinv, st)) != NIB_OK) return rc;
+  g.A = L + (size_t)(r0 + h) * ldl + r0; g.sai = 1; g.sat = ldl;        // A(i,t) = L[r0+h+t][r0+i]
+  g.B = B + (size_t)(r0 + h) * ldb;
+  g.C = B + (size_t)r0 * ldb;
+  g.M = h; g.K = nr - h;
+  if ((rc = dgemm_sub(g, st)) != NIB_OK) return rc;
+  return trsm_rec(L, ldl, B, nrhs, ldb, r0, h, trans, dinv, st);
+}
+
+static bool gp_v1() {
+  static const bool v = getenv("NIB_GP_V1") != nullptr;   // the two-level blocked solves of the first version (A/B timing)
+  return v;
+}
+
+static int trsm_impl(const double* L, int n, int ldl, double* B, int nrhs, int ldb, int trans, cudaStream_t st) {
+  if (n <= 0 || nrhs <= 0) return NIB_OK;
+  if (gp_v1()) return trsm_impl_v1(L, n, ldl, B, nrhs, ldb, trans, st);
+  int rc = ensure_dinv(n);
+  if (rc != NIB_OK) return rc;
+  if ((rc = trtri_attrs()) != NIB_OK) return rc;
+  trtri64_batched_kernel<<<ceil_div(n, NB), 256, TRTRI_SMEM, st>>>(L, ldl, n, g_dinv);
+  NIB_LAUNCH_CHECK();
+  if (nrhs == 1 && ldb == 1) return trsv_impl(L, n, ldl, B, trans, g_dinv, st);
+  return trsm_rec(L, ldl, B, nrhs, ldb, 0, n, trans, g_dinv, st);
+}
+
+
+// Recursive Cholesky: factor the leading half, solve the off-diagonal block against it (recursively: 64-wide leaves are
+// one product with inv(Lkk)^T, the rest is GEMM), subtract its Gram from the trailing half, recurse.  Same flops as the
+// right-looking sweep, but the symmetric updates run at depth w/2 instead of 64 / 256.
+static int rtrsm_rec(double* Kx, int ld, int c0, int w, int r0, int nr, const double* dinv, const int* info, cudaStream_t st) {
+  if (w <= NB) return apply_dinv(dinv + (size_t)(c0 / NB) * NB * NB, Kx, ld, c0, w, r0, nr, 2, info, st);
+  const int wa = split64(w);
+  int rc;
+  if ((rc = rtrsm_rec(Kx, ld, c0, wa, r0, nr, dinv, info, st)) != NIB_OK) return rc;
+  DgemmArgs g;
+  g.A = Kx + (size_t)r0 * ld + c0; g.sai = ld; g.sat = 1;                  // X1[i][t]
+  g.B = Kx + (size_t)(c0 + wa) * ld + c0; g.sbt = 1; g.sbj = ld;           // B(t,j) = L[c0+wa+j][c0+t]
+  g.C = Kx + (size_t)r0 * ld + c0 + wa; g.ldc = ld;
+  g.M = nr; g.N = w - wa; g.K = wa; g.lower_only = 0;
+  if ((rc = dgemm_sub(g, st)) != NIB_OK) return rc;
+  return rtrsm_rec(Kx, ld, c0 + wa, w - wa, r0, nr, dinv, info, st);
+}
+
+static int chol_rec(double* Kx, int ld, int k0, int w, double* dinv, int* info, cudaStream_t st) {
+  if (w <= NB) {
+    potrf_diag_kernel<<<1, 256, TRTRI_SMEM, st>>>(Kx, ld, k0, w, info, dinv + (size_t)(k0 / NB) * NB * NB);
+    NIB_LAUNCH_CHECK();
+    return NIB_OK;
+  }
+  const int wa = split64(w), wb = w - wa;
+  int rc;
+  if ((rc = chol_rec(Kx, ld, k0, wa, dinv, info, st)) != NIB_OK) return rc;
+  if ((rc = rtrsm_rec(Kx, ld, k0, wa, k0 + wa, wb, dinv, info, st)) != NIB_OK) return rc;
+  DgemmArgs g;
+  const double* X = Kx + (size_t)(k0 + wa) * ld + k0;
+  g.A = X; g.sai = ld; g.sat = 1;
+  g.B = X; g.sbt = 1; g.sbj = ld;
+  g.C = Kx + (size_t)(k0 + wa) * ld + (k0 + wa); g.ldc = ld;
+  g.M = wb; g.N = wb; g.K = wa; g.lower_only = 1;
+  if ((rc = dgemm_sub(g, st)) != NIB_OK) return rc;
+  return chol_rec(Kx, ld, k0 + wa, wb, dinv, info, st);
 }
 
 // ---- posterior pieces ------------------------------------------------------------------------
@@ -739,12 +1109,55 @@ int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream) {
   NIB_REQUIRE(d_K && d_info && n > 0 && ldk >= n, "nib_gp_cholesky: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   NIB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+  if (!gp_v1()) {
+    int rc = ensure_dinv(n);
+    if (rc != NIB_OK) return rc;
+    if ((rc = trtri_attrs()) != NIB_OK) return rc;
+    static const bool rec = getenv("NIB_GP_CHOL_REC") != nullptr;   // fully recursive variant: measured slower (its
+    if (rec) return chol_rec(d_K, ldk, 0, n, g_dinv, d_info, st);   // small symmetric updates leave most SMs idle)
+    // Right-looking, two-level: 64-wide steps inside NBC-wide super-blocks.  Each step factors the diagonal block AND
+    // inverts it (potrf_diag_kernel), turns the panel solve for every row below into one 64-deep product with that
+    // inverse (apply_dinv_kernel) and updates the rest of the super-block's columns (rank 64); everything to the right of
+    // the super-block gets one rank-NBC update.
+    for (int K0 = 0; K0 < n; K0 += NBC) {
+      const int W = min(NBC, n - K0);
+      for (int k0 = K0; k0 < K0 + W; k0 += NB) {
+        const int nb = min(NB, K0 + W - k0);
+        double* dk = g_dinv + (size_t)(k0 / NB) * NB * NB;
+        potrf_diag_kernel<<<1, 256, TRTRI_SMEM, st>>>(d_K, ldk, k0, nb, d_info, dk);
+        NIB_LAUNCH_CHECK();
+        const int below = n - (k0 + nb);
+        if (below > 0 && (rc = apply_dinv(dk, d_K, ldk, k0, nb, k0 + nb, below, 2, d_info, st)) != NIB_OK) return rc;
+        const int cols = K0 + W - (k0 + nb);
+        if (below > 0 && cols > 0) {
+          DgemmArgs g;
+          const double* X = d_K + (size_t)(k0 + nb) * ldk + k0;
+          g.A = X; g.sai = ldk; g.sat = 1;
+          g.B = X; g.sbt = 1; g.sbj = ldk;
+          g.C = d_K + (size_t)(k0 + nb) * ldk + (k0 + nb); g.ldc = ldk;
+          g.M = below; g.N = cols; g.K = nb; g.lower_only = 1;
+          if ((rc = dgemm_sub(g, st)) != NIB_OK) return rc;
+        }
+      }
+      const int below = n - (K0 + W);
+      if (below > 0) {
+        DgemmArgs g;
+        const double* X = d_K + (size_t)(K0 + W) * ldk + K0;
+        g.A = X; g.sai = ldk; g.sat = 1;
+        g.B = X; g.sbt = 1; g.sbj = ldk;
+        g.C = d_K + (size_t)(K0 + W) * ldk + (K0 + W); g.ldc = ldk;
+        g.M = below; g.N = below; g.K = W; g.lower_only = 1;
+        if ((rc = dgemm_sub(g, st)) != NIB_OK) return rc;
+      }
+    }
+    return NIB_OK;
+  }
   // right-looking, two-level: 64-wide panels inside 256-wide super-blocks (see trsm_impl for why)
   for (int K0 = 0; K0 < n; K0 += NBO) {
     const int W = min(NBO, n - K0);
     for (int k0 = K0; k0 < K0 + W; k0 += NB) {
       const int nb = min(NB, K0 + W - k0);
-      potrf_diag_kernel<<<1, 256, 0, st>>>(d_K, ldk, k0, nb, d_info);
+      potrf_diag_kernel<<<1, 256, 0, st>>>(d_K, ldk, k0, nb, d_info, nullptr);
       NIB_LAUNCH_CHECK();
       const int below = n - (k0 + nb);
       if (below > 0) {
