@@ -109,8 +109,11 @@ dgemm_sub_kernel(DgemmArgs g) {
   constexpr int ASP = GTM + 4;          // A pitch: = 8 words mod 32 for both tile heights
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (g.lower_only && bj * GT > bi * GTM + GTM - 1) return;
-  __shared__ __align__(16) double As[GK][ASP];
-  __shared__ __align__(16) double Bs[GK][GS];
+  // two smem stages (dynamic: 51 / 66 KB): global loads of chunk c+1 are issued before the MMAs of chunk c and parked
+  // after them, one __syncthreads per chunk
+  extern __shared__ __align__(16) double dg_smem[];
+  double (*As)[GK][ASP] = reinterpret_cast<double (*)[GK][ASP]>(dg_smem);
+  double (*Bs)[GK][GS] = reinterpret_cast<double (*)[GK][GS]>(dg_smem + 2 * GK * ASP);
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;          // warp tile: rows wm*GTM/2.., cols wn*32..
@@ -123,63 +126,63 @@ dgemm_sub_kernel(DgemmArgs g) {
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   // loader mapping: GTM x 16 elements of A and 128 x 16 of B per chunk; the fastest-varying thread index runs along the
-  // unit-stride direction of the operand so a warp reads whole 128 B lines.
+  // unit-stride direction of the operand so a warp reads whole 128 B lines.  Element pointers and row/column validity
+  // are fixed per thread; a chunk only adds k0 * stride (the per-element 64-bit index arithmetic of the first version
+  // cost as many instructions as the MMAs themselves).
   const bool a_t_fast = (g.sat == 1);
   const bool b_j_fast = (g.sbj == 1);
   double av[AE], bv[8];
-  auto a_pos = [&](int e, int& ii, int& tt) {
-    const int idx = tid + e * 256;
-    if (a_t_fast) { tt = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GTM - 1); tt = idx / GTM; }
-  };
-  auto b_pos = [&](int e, int& jj, int& tt) {
-    const int idx = tid + e * 256;
-    if (b_j_fast) { jj = idx & (GT - 1); tt = idx >> 7; } else { tt = idx & (GK - 1); jj = idx >> 4; }
-  };
+  // element e of a thread = element 0 shifted by e * (di rows, dt depth) — 256 threads tile the chunk in whole rows /
+  // columns — so one base pointer and one 64-bit step per operand describe all of them
+  constexpr int A_DI_T = 16, A_DT_I = 256 / GTM;    // a_t_fast: +16 rows per e;  otherwise: +256/GTM depth per e
+  const int a_i0 = a_t_fast ? (tid >> 4) : (tid & (GTM - 1));
+  const int a_t0 = a_t_fast ? (tid & (GK - 1)) : (tid / GTM);
+  const int a_di = a_t_fast ? A_DI_T : 0, a_dt = a_t_fast ? 0 : A_DT_I;
+  const int b_j0 = b_j_fast ? (tid & (GT - 1)) : (tid >> 4);
+  const int b_t0 = b_j_fast ? (tid >> 7) : (tid & (GK - 1));
+  const int b_dj = b_j_fast ? 0 : 16, b_dt = b_j_fast ? 2 : 0;
+  const double* ap0 = g.A + (long long)(i0 + a_i0) * g.sai + (long long)a_t0 * g.sat;
+  const long long astep = (long long)a_di * g.sai + (long long)a_dt * g.sat;
+  const double* bp0 = g.B + (long long)b_t0 * g.sbt + (long long)(j0 + b_j0) * g.sbj;
+  const long long bstep = (long long)b_dt * g.sbt + (long long)b_dj * g.sbj;
   auto load_chunk = [&](int k0) {
+    const double* pa = ap0 + (long long)k0 * g.sat;
+    const double* pb = bp0 + (long long)k0 * g.sbt;
 #pragma unroll
-    for (int e = 0; e < AE; ++e) {
-      int ii, tt;
-      a_pos(e, ii, tt);
-      const int gi = i0 + ii, gt = k0 + tt;
-      av[e] = (gi < g.M && gt < g.K) ? g.A[gi * g.sai + gt * g.sat] : 0.0;
-    }
+    for (int e = 0; e < AE; ++e)
+      av[e] = (i0 + a_i0 + e * a_di < g.M && k0 + a_t0 + e * a_dt < g.K) ? pa[e * astep] : 0.0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int jj, t2;
-      b_pos(e, jj, t2);
-      const int gj = j0 + jj, gt2 = k0 + t2;
-      bv[e] = (gj < g.N && gt2 < g.K) ? g.B[gt2 * g.sbt + gj * g.sbj] : 0.0;
-    }
+    for (int e = 0; e < 8; ++e)
+      bv[e] = (j0 + b_j0 + e * b_dj < g.N && k0 + b_t0 + e * b_dt < g.K) ? pb[e * bstep] : 0.0;
+  };
+  auto park = [&](int st) {
+#pragma unroll
+    for (int e = 0; e < AE; ++e) As[st][a_t0 + e * a_dt][a_i0 + e * a_di] = av[e];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Bs[st][b_t0 + e * b_dt][b_j0 + e * b_dj] = bv[e];
   };
   load_chunk(0);
+  park(0);
+  __syncthreads();
+  int cur = 0;
   for (int k0 = 0; k0 < g.K; k0 += GK) {
-    __syncthreads();   // everyone is done reading the previous chunk
-#pragma unroll
-    for (int e = 0; e < AE; ++e) {
-      int ii, tt;
-      a_pos(e, ii, tt);
-      As[tt][ii] = av[e];
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int jj, t2;
-      b_pos(e, jj, t2);
-      Bs[t2][jj] = bv[e];
-    }
-    __syncthreads();
-    if (k0 + GK < g.K) load_chunk(k0 + GK);
+    const bool more = k0 + GK < g.K;
+    if (more) load_chunk(k0 + GK);
 #pragma unroll
     for (int t = 0; t < GK; t += 4) {
       double a[MT], b[4];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) a[mt] = As[t + fk][wm * (GTM / 2) + mt * 8 + fr];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = As[cur][t + fk][wm * (GTM / 2) + mt * 8 + fr];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[t + fk][wn * 32 + nt * 8 + fr];
+      for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[cur][t + fk][wn * 32 + nt * 8 + fr];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
     }
+    if (more) park(cur ^ 1);     // the stage read two iterations ago: everyone passed the barrier that followed it
+    __syncthreads();
+    cur ^= 1;
   }
   // C -= acc.  Each thread owns column pairs (2fk, 2fk+1): one 16-byte access per pair, so the four lanes of a fragment
   // row cover a whole 64 B (two full sectors) — 8-byte accesses wrote every sector in four partial pieces and the
@@ -223,12 +226,19 @@ dgemm_sub_kernel(DgemmArgs g) {
   }
 }
 
+static constexpr size_t dgemm_smem(int gtm) { return (size_t)2 * GK * ((gtm + 4) + GS) * sizeof(double); }
 static int dgemm_sub(const DgemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return NIB_OK;
   static const int tile_m = [] { const char* e = getenv("NIB_GP_TILE_M"); return e && atoi(e) == 128 ? 128 : 64; }();
+  static bool attr = false;
+  if (!attr) {
+    NIB_CUDA(cudaFuncSetAttribute(dgemm_sub_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem(128)));
+    NIB_CUDA(cudaFuncSetAttribute(dgemm_sub_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem(64)));
+    attr = true;
+  }
   dim3 grid(ceil_div(g.N, GT), ceil_div(g.M, tile_m));
-  if (tile_m == 128) dgemm_sub_kernel<128><<<grid, 256, 0, st>>>(g);
-  else dgemm_sub_kernel<64><<<grid, 256, 0, st>>>(g);
+  if (tile_m == 128) dgemm_sub_kernel<128><<<grid, 256, dgemm_smem(128), st>>>(g);
+  else dgemm_sub_kernel<64><<<grid, 256, dgemm_smem(64), st>>>(g);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }
@@ -241,7 +251,9 @@ static int dgemm_sub(const DgemmArgs& g, cudaStream_t st) {
 // 4 x 4 diagonal blocks directly, then inv([[A,0],[B,C]]) = [[Ai,0],[-Ci*B*Ai,Ci]] for block sizes 4, 8, 16, 32 —
 // about 80 dependent operations in total.  Ls: the factor block (identity padded), Xs: the inverse (zeros above the
 // diagonal), both 64 x 65 in shared memory; called by all 256 threads.
-__device__ __forceinline__ void trtri64_coop(const double (*Ls)[NB + 1], double (*Xs)[NB + 1]) {
+__device__ __forceinline__ void trtri64_coop(const double (*Ls)[NB + 1], double (*Xs)[NB + 1], const double* rdiag) {
+  // rdiag[r] = 1 / Ls[r][r] (shared memory).  Every loop below has a uniform trip count — the zeros above the diagonal of
+  // Xs stand in for the triangular bounds — so a thread's elements advance together as independent FMA chains.
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NB * NB; idx += 256) Xs[idx >> 6][idx & 63] = 0.0;
   __syncthreads();
@@ -253,69 +265,62 @@ __device__ __forceinline__ void trtri64_coop(const double (*Ls)[NB + 1], double 
       double sacc = (r == c) ? 1.0 : 0.0;
 #pragma unroll
       for (int t = 0; t < r; ++t) sacc = fma(-Ls[b0 + r][b0 + t], x[t], sacc);
-      x[r] = (r >= c) ? sacc / Ls[b0 + r][b0 + r] : 0.0;
+      x[r] = (r >= c) ? sacc * rdiag[b0 + r] : 0.0;
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) Xs[b0 + r][b0 + c] = x[r];
   }
   __syncthreads();
-#pragma unroll 1
-  for (int sz = 4; sz < NB; sz *= 2) {
+#pragma unroll
+  for (int lv = 0; lv < 4; ++lv) {
+    const int sz = 4 << lv;                     // 4, 8, 16, 32 (compile-time after unrolling)
     const int per = sz * sz;                    // elements of one off-diagonal block
     const int total = (NB / (2 * sz)) * per;    // 32 * sz
-    // T = B * Ai, parked where the result block will live
-    double tv[4];
+    constexpr int EMAX = 4;
+    const int ne = (total + 255) / 256;         // elements per thread: 1, 1, 2, 4
+    int ri[EMAX], cj[EMAX], bs[EMAX];
+    double tv[EMAX];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < EMAX; ++e) {
       const int idx = tid + e * 256;
-      tv[e] = 0.0;
-      if (idx < total) {
-        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
+      const int pr = idx / per, w = idx - pr * per;
+      ri[e] = w / sz; cj[e] = w - ri[e] * sz; bs[e] = 2 * sz * pr;
+    }
+    // T = B * Ai, parked where the result block will live
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      if (e < ne && tid + e * 256 < total) {
         double a0 = 0.0, a1 = 0.0;
-        for (int t = j; t + 1 < sz; t += 2) {    // Ai is lower triangular: Ai[t][j] = 0 for t < j
-          a0 = fma(Ls[base + sz + i][base + t], Xs[base + t][base + j], a0);
-          a1 = fma(Ls[base + sz + i][base + t + 1], Xs[base + t + 1][base + j], a1);
+#pragma unroll 4
+        for (int t = 0; t < sz; t += 2) {
+          a0 = fma(Ls[bs[e] + sz + ri[e]][bs[e] + t], Xs[bs[e] + t][bs[e] + cj[e]], a0);
+          a1 = fma(Ls[bs[e] + sz + ri[e]][bs[e] + t + 1], Xs[bs[e] + t + 1][bs[e] + cj[e]], a1);
         }
-        if ((sz - j) & 1) a0 = fma(Ls[base + sz + i][base + sz - 1], Xs[base + sz - 1][base + j], a0);
         tv[e] = a0 + a1;
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;
-      if (idx < total) {
-        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
-        Xs[base + sz + i][base + j] = tv[e];
-      }
-    }
+    for (int e = 0; e < EMAX; ++e)
+      if (e < ne && tid + e * 256 < total) Xs[bs[e] + sz + ri[e]][bs[e] + cj[e]] = tv[e];
     __syncthreads();
     // O = -Ci * T
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;
-      tv[e] = 0.0;
-      if (idx < total) {
-        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
+    for (int e = 0; e < EMAX; ++e) {
+      if (e < ne && tid + e * 256 < total) {
         double a0 = 0.0, a1 = 0.0;
-        int t = 0;
-        for (; t + 1 <= i; t += 2) {             // Ci[i][t] = 0 for t > i
-          a0 = fma(Xs[base + sz + i][base + sz + t], Xs[base + sz + t][base + j], a0);
-          a1 = fma(Xs[base + sz + i][base + sz + t + 1], Xs[base + sz + t + 1][base + j], a1);
+#pragma unroll 4
+        for (int t = 0; t < sz; t += 2) {
+          a0 = fma(Xs[bs[e] + sz + ri[e]][bs[e] + sz + t], Xs[bs[e] + sz + t][bs[e] + cj[e]], a0);
+          a1 = fma(Xs[bs[e] + sz + ri[e]][bs[e] + sz + t + 1], Xs[bs[e] + sz + t + 1][bs[e] + cj[e]], a1);
         }
-        if (t <= i) a0 = fma(Xs[base + sz + i][base + sz + t], Xs[base + sz + t][base + j], a0);
         tv[e] = -(a0 + a1);
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;
-      if (idx < total) {
-        const int pr = idx / per, w = idx - pr * per, i = w / sz, j = w - i * sz, base = 2 * sz * pr;
-        Xs[base + sz + i][base + j] = tv[e];
-      }
-    }
+    for (int e = 0; e < EMAX; ++e)
+      if (e < ne && tid + e * 256 < total) Xs[bs[e] + sz + ri[e]][bs[e] + cj[e]] = tv[e];
     __syncthreads();
   }
 }
@@ -330,12 +335,22 @@ trtri64_batched_kernel(const double* __restrict__ Lm, int ldl, int n, double* __
   double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tt_smem + NB * (NB + 1));
   const int k0 = blockIdx.x * NB;
   const int nb = min(NB, n - k0);
-  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
-    const int i = idx >> 6, j = idx & 63;
-    Ls[i][j] = (i < nb && j <= i) ? Lm[(size_t)(k0 + i) * ldl + k0 + j] : ((i == j) ? 1.0 : 0.0);
+  double lv[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int idx = threadIdx.x + e * 256, i = idx >> 6, j = idx & 63;
+    lv[e] = (i < nb && j <= i) ? Lm[(size_t)(k0 + i) * ldl + k0 + j] : ((i == j) ? 1.0 : 0.0);
   }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int idx = threadIdx.x + e * 256;
+    Ls[idx >> 6][idx & 63] = lv[e];
+  }
+  __shared__ double rdiag[NB];
   __syncthreads();
-  trtri64_coop(Ls, Xs);
+  if (threadIdx.x < NB) rdiag[threadIdx.x] = 1.0 / Ls[threadIdx.x][threadIdx.x];
+  __syncthreads();
+  trtri64_coop(Ls, Xs, rdiag);
   double* out = dinv + (size_t)blockIdx.x * NB * NB;
   for (int idx = threadIdx.x; idx < NB * NB; idx += 256) out[idx] = Xs[idx >> 6][idx & 63];
 }
@@ -459,6 +474,7 @@ static inline int split64(int w) { return ((w / 2 + NB - 1) / NB) * NB; }   // N
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restrict__ info, double* __restrict__ dinv) {
   __shared__ double colbuf[2][NB];
+  __shared__ double rdiag[NB];
   extern __shared__ __align__(16) double pd_smem[];   // the factored block and its inverse (dinv != null), TRTRI_SMEM bytes
   double (*Lsh)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(pd_smem);
   double (*Xsh)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(pd_smem + NB * (NB + 1));
@@ -491,11 +507,11 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restric
       if (tid == 0 && *info == 0) *info = k0 + j + 1;
       return;
     }
-    // one reciprocal square root (Newton-refined) instead of a square root followed by a division: the pivot chain is
+    // one reciprocal square root instead of a square root followed by a division: the pivot chain is
     // 64 steps long and every dependent fp64 operation on it costs ~48 cycles
-    double inv = rsqrt(d);
-    inv = fma(inv * 0.5, fma(-d * inv, inv, 1.0), inv);   // one more Newton step: full double precision
+    const double inv = rsqrt(d);      // CUDA's double rsqrt is accurate to 1 ulp
     const double rs = d * inv;
+    if (tid == 0) rdiag[j] = inv;     // = 1 / L[j][j], reused by the inverse
     double lr[4], lc[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -521,7 +537,7 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restric
     }
   if (dinv == nullptr) return;
   __syncthreads();
-  trtri64_coop(Lsh, Xsh);
+  trtri64_coop(Lsh, Xsh, rdiag);
   for (int idx = tid; idx < NB * NB; idx += 256) dinv[idx] = Xsh[idx >> 6][idx & 63];
 }
 
@@ -736,7 +752,7 @@ static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, cons
 // per super-block.  The trailing GEMM is read-modify-write on its output: at K = 64 it measured 8-9 TFLOP/s (the tile's
 // C round trip dominates), at K = 256 17 TFLOP/s, at large K 25.7 of the 37 TFLOP/s DMMA peak (tools/gp_profile.py).
 static constexpr int NBO = 256;
-static const int NBC = [] { const char* e = getenv("NIB_GP_NBC"); const int v = e ? atoi(e) : 256; return v >= 64 && v % 64 == 0 ? v : 256; }();   // Cholesky super-block width
+static const int NBC = [] { const char* e = getenv("NIB_GP_NBC"); const int v = e ? atoi(e) : 512; return v >= 64 && v % 64 == 0 ? v : 512; }();   // Cholesky super-block width (measured at n = 8192: 128 -> 21.1, 256 -> 20.7, 512 -> 20.4 ms fit)
 
 static int trsm_impl_v1(const double* L, int n, int ldl, double* B, int nrhs, int ldb, int trans, cudaStream_t st) {
   if (n <= 0 || nrhs <= 0) return NIB_OK;
