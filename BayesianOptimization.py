@@ -101,9 +101,24 @@ def bayesian_optimisation_masks(n_iters, score_masks, train_bits, train_scores, 
     Z = np.ascontiguousarray(train_bits, dtype=np.uint64).copy()
     y = np.asarray(train_scores, dtype=np.float64).copy()
     cand = np.ascontiguousarray(candidate_bits, dtype=np.uint64)
+    history = []
+    if length_scale is not None and not refit_every:
+        # fixed length scale: the Gram matrix of the points already seen never changes, so each round is a rank-one update
+        # of the factor and of the posterior workspace (ActiveMaskGP) instead of an O(n^3 + m n^2) refit
+        gp = _gp.ActiveMaskGP(cand, alpha=alpha, length_scale=length_scale, normalize_y=True, capacity=n_iters).fit(Z, y)
+        for it in range(n_iters):
+            mu, var, sd = gp.posterior()
+            ei, arg = _gp.expected_improvement_device(mu, sd, float(np.max(gp.y_host)), True)
+            j = int(arg.item())
+            if j < 0:   # every EI is NaN (all sigma == 0): fall back to a random candidate like reference :178-180
+                alive = np.nonzero(gp.alive.cpu().numpy())[0]
+                j = int(alive[np.random.RandomState(random_state + it).randint(len(alive))])
+            s = float(np.asarray(score_masks(cand[j:j + 1]))[0])
+            history.append({"round": it, "candidate": j, "ei": float(ei[j].item()), "score": s, "length_scale": length_scale})
+            gp.append(j, s)
+        return np.concatenate([Z, cand[[h["candidate"] for h in history]]], 0), np.asarray(gp.y_host), history
     alive = np.ones(cand.shape[0], dtype=bool)
     ell = length_scale
-    history = []
     for it in range(n_iters):
         optimise = ell is None or (refit_every and it % refit_every == 0 and it > 0)
         gp = GaussianProcessRegressor(alpha=alpha, normalize_y=True, length_scale=ell or 1.0,
@@ -124,5 +139,4 @@ def bayesian_optimisation_masks(n_iters, score_masks, train_bits, train_scores, 
         Z = np.concatenate([Z, cand[pick:pick + 1]], 0)
         y = np.concatenate([y, [s]])
         del gp
-        torch.cuda.empty_cache()
     return Z, y, history

@@ -271,6 +271,18 @@ int nib_gp_lml_grad_rbf(const double* d_K0, const double* d_Kinv, const double* 
                         const double* d_X, int d, int n, int ld, double length_scale,
                         double* h_grad, void* stream);
 
+/* Rank-one maintenance of the posterior workspace, for acquisition loops that add ONE training mask per round
+ * (bayesian_active_learning_imagenet.py / BayesianOptimization.py:140-185 refit the GP from scratch every round).
+ * With V = L^-1 K*^T [n x m] resident, appending a point needs l = L^-1 k (nib_gp_trsm, one vector), d = sqrt(k_nn +
+ * alpha - l.l), the new row of V: (k*_new - l^T V) / d, and sum-of-squares += row^2 — O(n^2 + m n) instead of O(n^3 + m n^2).
+ *   nib_gp_gemv_t      d_out[j] = sum_t d_x[t] * d_V[t*ldv + j]            (t < n, j < m)
+ *   nib_gp_colsumsq    d_out[j] = sum_t d_V[t*ldv + j]^2
+ *   nib_gp_append_row  v = (d_ks - d_dot) / d;  d_vrow = v;  d_ssq += v^2    (all length m) */
+int nib_gp_gemv_t(const double* d_V, int n, int m, int ldv, const double* d_x, double* d_out, void* stream);
+int nib_gp_colsumsq(const double* d_V, int n, int m, int ldv, double* d_out, void* stream);
+int nib_gp_append_row(const double* d_ks, const double* d_dot, double d, double* d_vrow, double* d_ssq, int m,
+                      void* stream);
+
 /* Expected improvement, BayesianOptimization.py:37-54 (returns +EI; the reference returns -EI):
  *   s = greater_is_better ? 1 : -1;  Z = s*(mu-best)/sigma;  EI = s*(mu-best)*Phi(Z)+sigma*phi(Z)
  * sigma == 0 yields NaN exactly as the reference (its `== 0.0` line :52 is a no-op comparison).

@@ -9,10 +9,10 @@ from . import _lib  # noqa: F401
 from .masks import KEEP_MUL, REMOVE_MINMAX, MaskSynth, draw_selections, selection_bits, prep_minmax_u8  # noqa: F401
 from .classifier import Classifier  # noqa: F401
 from .scoring import score  # noqa: F401
-from .gp import GaussianProcessRegressor, expected_improvement, expected_improvement_device  # noqa: F401
+from .gp import ActiveMaskGP, GaussianProcessRegressor, expected_improvement, expected_improvement_device  # noqa: F401
 from .engine import PerturbationEngine, shard_range, gather_scores  # noqa: F401
 from .pipeline import felzenszwalb, img_as_float, segment_image  # noqa: F401
 
-__all__ = ["MaskSynth", "Classifier", "score", "GaussianProcessRegressor", "expected_improvement",
+__all__ = ["MaskSynth", "Classifier", "score", "GaussianProcessRegressor", "ActiveMaskGP", "expected_improvement",
            "expected_improvement_device", "PerturbationEngine", "draw_selections", "selection_bits",
            "prep_minmax_u8", "felzenszwalb", "img_as_float", "segment_image", "shard_range", "gather_scores", "KEEP_MUL", "REMOVE_MINMAX"]

@@ -87,6 +87,9 @@ _PROTOTYPES = {
     "nib_gp_lml_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, C.POINTER(_d), _vp]),
     "nib_gp_lml_grad_rbf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, C.POINTER(_d), _vp]),
     "nib_gp_ei": (_i, [_vp, _vp, _i, _d, _i, _vp, _vp, _vp]),
+    "nib_gp_gemv_t": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "nib_gp_colsumsq": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "nib_gp_append_row": (_i, [_vp, _vp, _d, _vp, _vp, _i, _vp]),
     "nib_heatmap": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "nib_felzenszwalb": (_i, [_vp, _i, _i, _i, _d, _d, _i, _vp, C.POINTER(_i)]),
 }

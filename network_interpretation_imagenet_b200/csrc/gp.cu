@@ -959,6 +959,77 @@ colsumsq_var_kernel(const double* __restrict__ V, int n, int m, double prior_var
   if (sd) sd[q] = sqrt(r);
 }
 
+// ---- column reductions over V [n][m] (row-major): one pass over HBM, rows split into slices so the grid fills the GPU --
+// mode 0: partial[s][j] = sum_t x[t] * V[t][j];  mode 1: partial[s][j] = sum_t V[t][j]^2   (t in slice s)
+static constexpr int CR_ROWS = 64;   // rows per slice
+__global__ void __launch_bounds__(256)
+colreduce_partial_kernel(const double* __restrict__ V, long long ldv, int n, int m, const double* __restrict__ x, int mode,
+                         double* __restrict__ partial) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int t0 = blockIdx.y * CR_ROWS, t1 = min(n, t0 + CR_ROWS);
+  if (j >= m) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int t = t0;
+  for (; t + 3 < t1; t += 4) {
+    const double v0 = V[(size_t)t * ldv + j], v1 = V[(size_t)(t + 1) * ldv + j];
+    const double v2 = V[(size_t)(t + 2) * ldv + j], v3 = V[(size_t)(t + 3) * ldv + j];
+    if (mode == 0) { a0 = fma(x[t], v0, a0); a1 = fma(x[t + 1], v1, a1); a2 = fma(x[t + 2], v2, a2); a3 = fma(x[t + 3], v3, a3); }
+    else { a0 = fma(v0, v0, a0); a1 = fma(v1, v1, a1); a2 = fma(v2, v2, a2); a3 = fma(v3, v3, a3); }
+  }
+  for (; t < t1; ++t) {
+    const double v0 = V[(size_t)t * ldv + j];
+    a0 = (mode == 0) ? fma(x[t], v0, a0) : fma(v0, v0, a0);
+  }
+  partial[(size_t)blockIdx.y * m + j] = (a0 + a1) + (a2 + a3);
+}
+// out[j] = sum_s partial[s][j] (fixed order: deterministic); var/sd epilogue of _gpr.py:485-496 when var_mode
+__global__ void __launch_bounds__(256)
+colreduce_final_kernel(const double* __restrict__ partial, int slices, int m, double* __restrict__ out, int var_mode,
+                       double prior_var, double y_std, double* __restrict__ sd) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= m) return;
+  double acc = 0.0;
+  for (int sidx = 0; sidx < slices; ++sidx) acc += partial[(size_t)sidx * m + j];
+  if (var_mode) {
+    double r = prior_var - acc;
+    if (r < 0.0) r = 0.0;
+    r = r * y_std * y_std;
+    if (out) out[j] = r;
+    if (sd) sd[j] = sqrt(r);
+  } else {
+    out[j] = acc;
+  }
+}
+static double* g_cr = nullptr;
+static size_t g_cr_cap = 0;
+static int colreduce(const double* V, long long ldv, int n, int m, const double* x, int mode, double* out, int var_mode,
+                     double prior_var, double y_std, double* sd, cudaStream_t st) {
+  const int slices = ceil_div(n, CR_ROWS);
+  const size_t need = (size_t)slices * m;
+  if (g_cr_cap < need) {
+    if (g_cr) cudaFree(g_cr);
+    g_cr_cap = need < ((size_t)1 << 21) ? ((size_t)1 << 21) : need;
+    NIB_CUDA(cudaMalloc(&g_cr, g_cr_cap * sizeof(double)));
+  }
+  dim3 grid(ceil_div(m, 256), slices);
+  colreduce_partial_kernel<<<grid, 256, 0, st>>>(V, ldv, n, m, x, mode, g_cr);
+  NIB_LAUNCH_CHECK();
+  colreduce_final_kernel<<<ceil_div(m, 256), 256, 0, st>>>(g_cr, slices, m, out, var_mode, prior_var, y_std, sd);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+// rank-one extension of the posterior workspace (ActiveMaskGP.append): v = (ks - dot) / d becomes row n of V, ssq += v^2
+__global__ void __launch_bounds__(256)
+append_row_kernel(const double* __restrict__ ks, const double* __restrict__ dot, double d, double* __restrict__ vrow,
+                  double* __restrict__ ssq, int m) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= m) return;
+  const double v = (ks[j] - dot[j]) / d;
+  vrow[j] = v;
+  ssq[j] = fma(v, v, ssq[j]);
+}
+
 // ---- LML -------------------------------------------------------------------------------------
 __global__ void lml_kernel(const double* __restrict__ L, int n, int ldl, const double* __restrict__ y,
                            const double* __restrict__ alpha, double* __restrict__ out) {
@@ -1243,9 +1314,29 @@ int nib_gp_posterior(const double* d_L, int n, int ldl, const double* d_alpha, c
     NIB_LAUNCH_CHECK();
     int rc = trsm_impl(d_L, n, ldl, d_work, m, m, 0, st);
     if (rc != NIB_OK) return rc;
-    colsumsq_var_kernel<<<ceil_div(m, 256), 256, 0, st>>>(d_work, n, m, prior_var, y_std, d_var, d_std);
-    NIB_LAUNCH_CHECK();
+    if ((rc = colreduce(d_work, m, n, m, nullptr, 1, d_var, 1, prior_var, y_std, d_std, st)) != NIB_OK) return rc;
   }
+  return NIB_OK;
+}
+
+int nib_gp_gemv_t(const double* d_V, int n, int m, int ldv, const double* d_x, double* d_out, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_V && d_x && d_out && n > 0 && m > 0 && ldv >= m, "nib_gp_gemv_t: bad arguments");
+  return colreduce(d_V, ldv, n, m, d_x, 0, d_out, 0, 0.0, 1.0, nullptr, (cudaStream_t)stream);
+}
+
+int nib_gp_colsumsq(const double* d_V, int n, int m, int ldv, double* d_out, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_V && d_out && n > 0 && m > 0 && ldv >= m, "nib_gp_colsumsq: bad arguments");
+  return colreduce(d_V, ldv, n, m, nullptr, 1, d_out, 0, 0.0, 1.0, nullptr, (cudaStream_t)stream);
+}
+
+int nib_gp_append_row(const double* d_ks, const double* d_dot, double d, double* d_vrow, double* d_ssq, int m,
+                      void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_ks && d_dot && d_vrow && d_ssq && m > 0 && d > 0.0, "nib_gp_append_row: bad arguments");
+  append_row_kernel<<<ceil_div(m, 256), 256, 0, (cudaStream_t)stream>>>(d_ks, d_dot, d, d_vrow, d_ssq, m);
+  NIB_LAUNCH_CHECK();
   return NIB_OK;
 }
 

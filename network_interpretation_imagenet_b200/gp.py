@@ -211,6 +211,113 @@ class GaussianProcessRegressor:
         return mu.cpu().numpy()
 
 
+class ActiveMaskGP:
+    """The GP of an acquisition loop over a FIXED candidate pool, maintained by rank-one updates.
+
+    The reference's loop (BayesianOptimization.py:140-185, bayesian_active_learning_imagenet.py) refits the GP and
+    re-predicts every candidate each round: O(n^3 + m n^2).  With a fixed length scale the Gram matrix of the first n
+    points never changes, so adding the chosen candidate only borders the Cholesky factor by one row, and the posterior
+    workspace V = L^-1 K*^T gains one row:
+
+        l = L^-1 k(X, z)          d = sqrt(1 + alpha - l.l)          L <- [[L, 0], [l^T, d]]
+        V <- [V; (k*(z) - l^T V) / d]        ssq += (new row)^2        u <- [u; (y - l.u)/d]    w <- [w; (1 - l.w)/d]
+
+    and   mu = ybar + V^T (u - ybar w),   var = ystd^2 max(0, 1 - ssq)   (u = L^-1 y, w = L^-1 1: y-normalisation,
+    _gpr.py:276-280, changes every round but stays an O(n) correction).  O(n^2 + m n) per round; same posterior as a
+    refit up to rounding (tests/test_gpu_gp.py compares the two and the scikit-learn oracle)."""
+
+    def __init__(self, candidate_bits, alpha: float = 1e-5, length_scale: float = 1.0, normalize_y: bool = True,
+                 capacity: int = 64, device="cuda"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.alpha, self.ell, self.normalize_y, self.capacity = float(alpha), float(length_scale), normalize_y, int(capacity)
+        cand = np.ascontiguousarray(candidate_bits, dtype=np.uint64)
+        self.m, self.words = int(cand.shape[0]), int(cand.shape[1])
+        self.cand_host = cand
+        self.cand_d = torch.from_numpy(cand.view(np.int64)).to(self.device)
+        self.alive = torch.ones(self.m, dtype=torch.bool, device=self.device)
+
+    def _gram(self, A, na, B, nb, jitter, out, ld):
+        _lib.check(self.lib.nib_gp_gram_binary(A.data_ptr(), na, B.data_ptr(), nb, self.words, self.ell, jitter,
+                                               out.data_ptr(), ld, _lib.stream_handle()), "nib_gp_gram_binary")
+
+    def fit(self, Z_bits, y):
+        Z = np.ascontiguousarray(Z_bits, dtype=np.uint64)
+        n, cap, m, dev = int(Z.shape[0]), int(Z.shape[0]) + self.capacity, self.m, self.device
+        st = _lib.stream_handle()
+        self.n, self.cap = n, cap
+        self.X_d = torch.zeros(cap, self.words, dtype=torch.int64, device=dev)
+        self.X_d[:n] = torch.from_numpy(Z.view(np.int64)).to(dev)
+        self.y_host = list(np.asarray(y, dtype=np.float64).reshape(-1))
+        self.L = torch.zeros(cap, cap, dtype=torch.float64, device=dev)
+        self.V = torch.empty(cap, m, dtype=torch.float64, device=dev)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._gram(self.X_d, n, self.X_d, n, self.alpha, self.L, cap)
+        _lib.check(self.lib.nib_gp_cholesky(self.L.data_ptr(), n, cap, self.info.data_ptr(), st), "nib_gp_cholesky")
+        if int(self.info.item()) != 0:
+            raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix")
+        self._gram(self.X_d, n, self.cand_d, m, 0.0, self.V, m)                       # K*^T  [n x m]
+        _lib.check(self.lib.nib_gp_trsm(self.L.data_ptr(), n, cap, self.V.data_ptr(), m, m, 0, st), "nib_gp_trsm")
+        self.ssq = torch.empty(m, dtype=torch.float64, device=dev)
+        _lib.check(self.lib.nib_gp_colsumsq(self.V.data_ptr(), n, m, m, self.ssq.data_ptr(), st), "nib_gp_colsumsq")
+        self.uw = torch.zeros(2, cap, dtype=torch.float64, device=dev)               # u = L^-1 y, w = L^-1 1
+        self.uw[0, :n] = torch.as_tensor(np.asarray(self.y_host), device=dev)
+        self.uw[1, :n] = 1.0
+        for r in range(2):
+            _lib.check(self.lib.nib_gp_trsm(self.L.data_ptr(), n, cap, self.uw[r].data_ptr(), 1, 1, 0, st), "nib_gp_trsm")
+        self._tmp = torch.empty(3, max(m, cap), dtype=torch.float64, device=dev)
+        return self
+
+    def _ystats(self):
+        y = np.asarray(self.y_host)
+        if not self.normalize_y:
+            return 0.0, 1.0
+        sd = float(np.std(y))
+        return float(np.mean(y)), (sd if sd != 0.0 else 1.0)
+
+    def posterior(self):
+        """(mu, var, std) over the whole candidate pool, fp64 on the device; candidates already used carry std = NaN so
+        that Expected Improvement skips them (the reference's duplicate guard, BayesianOptimization.py:178-180)."""
+        n, m, st = self.n, self.m, _lib.stream_handle()
+        ybar, ystd = self._ystats()
+        z = self._tmp[0, :n]
+        torch.sub(self.uw[0, :n], self.uw[1, :n], alpha=ybar, out=z)                  # ystd * L^-1 y_normalised
+        mu = torch.empty(m, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.nib_gp_gemv_t(self.V.data_ptr(), n, m, m, z.data_ptr(), mu.data_ptr(), st), "nib_gp_gemv_t")
+        mu += ybar
+        var = (1.0 - self.ssq).clamp_(min=0.0) * (ystd * ystd)
+        sd = var.sqrt()
+        sd[~self.alive] = float("nan")
+        return mu, var, sd
+
+    def append(self, index: int, y_new: float):
+        """Candidate `index` has been evaluated: it joins the training set (and leaves the pool)."""
+        if self.n >= self.cap:
+            raise RuntimeError("ActiveMaskGP capacity exhausted: construct with a larger `capacity`")
+        n, m, cap, st = self.n, self.m, self.cap, _lib.stream_handle()
+        znew = self.cand_d[index:index + 1]
+        l = self.L[n, :n]                                                            # row n of L, filled in place
+        self._gram(znew, 1, self.X_d, n, 0.0, l, cap)                                # k(z, X)  [1 x n]
+        _lib.check(self.lib.nib_gp_trsm(self.L.data_ptr(), n, cap, l.data_ptr(), 1, 1, 0, st), "nib_gp_trsm")
+        d2 = 1.0 + self.alpha - float(torch.dot(l, l).item())
+        if not d2 > 0.0:
+            raise np.linalg.LinAlgError("rank-one update lost positive definiteness (duplicate mask with alpha too small?)")
+        d = float(np.sqrt(d2))
+        self.L[n, n] = d
+        ks, dot = self._tmp[1, :m], self._tmp[2, :m]
+        self._gram(self.cand_d, m, znew, 1, 0.0, ks, 1)                              # k*(z)  [m x 1]
+        _lib.check(self.lib.nib_gp_gemv_t(self.V.data_ptr(), n, m, m, l.data_ptr(), dot.data_ptr(), st), "nib_gp_gemv_t")
+        _lib.check(self.lib.nib_gp_append_row(ks.data_ptr(), dot.data_ptr(), d, self.V[n].data_ptr(),
+                                              self.ssq.data_ptr(), m, st), "nib_gp_append_row")
+        lu = torch.mv(self.uw[:, :n], l)                                              # (l.u, l.w)
+        self.uw[0, n] = (float(y_new) - lu[0]) / d
+        self.uw[1, n] = (1.0 - lu[1]) / d
+        self.X_d[n] = self.cand_d[index]
+        self.y_host.append(float(y_new))
+        self.alive[index] = False
+        self.n = n + 1
+
+
 def expected_improvement_device(mu: torch.Tensor, sigma: torch.Tensor, best: float, greater_is_better: bool = False):
     """+EI and its argmax on the device (BayesianOptimization.py:37-54 returns -EI)."""
     lib = _lib.load()

@@ -124,3 +124,57 @@ def test_cholesky_round_trip_large(nib):
     # training points are interpolated up to the jitter
     mu, sd = gp.predict(Z[:64], return_std=True)
     assert np.abs(mu - y[:64]).max() < 1e-2 and sd.max() < 0.05
+
+
+@pytest.mark.parametrize("n0,m,rounds", [(5, 40, 12), (200, 300, 70), (1000, 513, 5)])
+def test_rank_one_acquisition_updates_equal_refit_and_oracle(nib, n0, m, rounds):
+    """ActiveMaskGP: `rounds` appended candidates (crossing 64-row block boundaries) == a from-scratch fit on the grown
+    training set, both ours and the scikit-learn-pinned oracle; used candidates are masked out of the pool."""
+    S, ell = 50, 3.0
+    rng = np.random.RandomState(n0 + m)
+    sels, seen = [], set()
+    while len(sels) < n0 + m:                       # distinct masks (a duplicate makes K singular up to alpha)
+        s = tuple(sorted(rng.choice(S - 1, size=20, replace=False)))
+        if s not in seen:
+            seen.add(s)
+            sels.append(list(s))
+    Z = om.selection_bits(sels, S)
+    y0 = rng.rand(n0)
+    agp = nib.ActiveMaskGP(Z[n0:], alpha=1e-5, length_scale=ell, capacity=rounds).fit(Z[:n0], y0)
+    picks = [int(p) for p in rng.choice(m, size=rounds, replace=False)]
+    ynew = rng.rand(rounds)
+    for p, yv in zip(picks, ynew):
+        agp.append(p, float(yv))
+    mu, var, sd = (t.cpu().numpy() for t in agp.posterior())
+    Zt = np.concatenate([Z[:n0], Z[n0:][picks]], 0)
+    yt = np.concatenate([y0, ynew])
+    fit = ogp.gp_fit(ogp.bits_to_matrix(Zt, S), yt, ell)
+    mu0, var0, sd0 = ogp.gp_predict(fit, ogp.bits_to_matrix(Z[n0:], S))
+    live = np.ones(m, bool)
+    live[picks] = False
+    assert np.isnan(sd[~live]).all() and not np.isnan(sd[live]).any()
+    assert np.abs(mu - mu0).max() <= TOL and np.abs(var - var0).max() <= TOL
+    np.testing.assert_allclose(mu, mu0, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(sd[live], sd0[live], rtol=1e-4, atol=1e-6)
+    ref = nib.GaussianProcessRegressor(alpha=1e-5, length_scale=ell, optimizer=None).fit(Zt, yt)
+    mu1, var1, _ = (t.cpu().numpy() for t in ref.predict_device(Z[n0:]))
+    np.testing.assert_allclose(mu, mu1, rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(var, var1, rtol=1e-5, atol=1e-9)
+    with pytest.raises(RuntimeError):
+        agp.append(int(np.nonzero(live)[0][0]), 0.5)   # capacity exhausted
+
+
+def test_bo_loop_rank_one_path_picks_the_same_candidates_as_refitting(nib):
+    import BayesianOptimization as bo
+    S, n0, m = 50, 150, 200
+    rng = np.random.RandomState(3)
+    sels = [list(rng.choice(S - 1, size=20, replace=False)) for _ in range(n0 + m)]
+    Z = om.selection_bits(sels, S)
+    w = rng.rand(S)
+    score = lambda b: np.array([float(sum(w[s] for s in range(S) if (int(v[0]) >> s) & 1)) / 10.0 for v in b])
+    y0 = score(Z[:n0])
+    _, ya, ha = bo.bayesian_optimisation_masks(8, score, Z[:n0], y0, Z[n0:], length_scale=3.0)
+    _, yb, hb = bo.bayesian_optimisation_masks(8, score, Z[:n0], y0, Z[n0:], length_scale=3.0, refit_every=10 ** 9)
+    assert [h["candidate"] for h in ha] == [h["candidate"] for h in hb]
+    np.testing.assert_allclose(ya, yb)
+    np.testing.assert_allclose([h["ei"] for h in ha], [h["ei"] for h in hb], rtol=1e-5, atol=1e-9)
