@@ -335,29 +335,45 @@ def _lower_tv_resnet(m, hw, prec, precision, max_batch):
 def _lower_resnet_cifar(m, hw, prec, precision, max_batch):
     H, W = hw
     b = _Builder(prec, max_batch)
+    # bf16: every activation carries at least 64 physical channels (zero weights / biases for the padding), which puts
+    # the 16- and 32-channel stages on the tcgen05 implicit-GEMM path (K atom = 64 channels) instead of the CUDA-core
+    # kernel: 4x / 2x redundant MACs on zeros, still ~3.5x faster end to end (profiles/README.md, configs[1]).
+    cp = (lambda c: max(c, 64)) if precision == "bf16" else (lambda c: c)
+
+    def padw(w, bias, co, ci):
+        if co == w.shape[0] and ci == w.shape[1]:
+            return w, bias
+        wp = torch.zeros(co, ci, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+        wp[:w.shape[0], :w.shape[1]] = w
+        bp = None
+        if bias is not None:
+            bp = torch.zeros(co, dtype=bias.dtype, device=bias.device)
+            bp[:bias.shape[0]] = bias
+        return wp, bp
+
     x_in = b.buffer(H, W, _in_cpad(3), pooled=False)
-    x = b.buffer(H, W, 16)
-    w, bias = fold_bn(m.conv1.weight, None, m.bn1)
-    b.conv(x_in, 3, x, 16, w, bias, 3, 1, 1, relu=True)
+    x = b.buffer(H, W, cp(16))
+    w, bias = padw(*fold_bn(m.conv1.weight, None, m.bn1), cp(16), 3)
+    b.conv(x_in, 3, x, cp(16), w, bias, 3, 1, 1, relu=True)
     Cx, Hx, Wx = 16, H, W
     for layer in (m.layer1, m.layer2, m.layer3):
         for blk in layer:
             s = blk.conv1.stride[0]
             planes = blk.conv1.out_channels
             Ho, Wo = _out_hw(Hx, 3, s, 1), _out_hw(Wx, 3, s, 1)
-            t = b.buffer(Ho, Wo, planes)
-            w, bias = fold_bn(blk.conv1.weight, None, blk.bn1)
-            b.conv(x, Cx, t, planes, w, bias, 3, s, 1, relu=True)          # conv1 takes the un-downsampled x (:33)
+            t = b.buffer(Ho, Wo, cp(planes))
+            w, bias = padw(*fold_bn(blk.conv1.weight, None, blk.bn1), cp(planes), cp(Cx))
+            b.conv(x, cp(Cx), t, cp(planes), w, bias, 3, s, 1, relu=True)  # conv1 takes the un-downsampled x (:33)
             if blk.downsample is not None:                                 # DownsampleB: avgpool + zero channels
                 ks = blk.downsample.avg.kernel_size
                 ks = ks if isinstance(ks, int) else ks[0]
-                idn = b.buffer(_out_hw(Hx, ks, ks, 0), _out_hw(Wx, ks, ks, 0), Cx)
-                b.pool(_lib.POOL_AVG, x, Cx, idn, ks, ks, 0)
+                idn = b.buffer(_out_hw(Hx, ks, ks, 0), _out_hw(Wx, ks, ks, 0), cp(Cx))
+                b.pool(_lib.POOL_AVG, x, cp(Cx), idn, ks, ks, 0)
             else:
                 idn = x
-            o = b.buffer(Ho, Wo, planes)
-            w, bias = fold_bn(blk.conv2.weight, None, blk.bn2)
-            b.conv(t, planes, o, planes, w, bias, 3, 1, 1, relu=True, res=idn, res_C=Cx)
+            o = b.buffer(Ho, Wo, cp(planes))
+            w, bias = padw(*fold_bn(blk.conv2.weight, None, blk.bn2), cp(planes), cp(planes))
+            b.conv(t, cp(planes), o, cp(planes), w, bias, 3, 1, 1, relu=True, res=idn, res_C=cp(Cx))
             b.release(t)
             if idn != x:
                 b.release(idn)
@@ -366,9 +382,13 @@ def _lower_resnet_cifar(m, hw, prec, precision, max_batch):
     ks = m.avgpool.kernel_size
     ks = ks if isinstance(ks, int) else ks[0]
     assert _out_hw(Hx, ks, ks, 0) == 1, "AvgPool2d(8) must reduce to 1x1 (models/resnet.py:103)"
-    feat = b.buffer(1, 1, Cx)
-    b.pool(_lib.POOL_AVG, x, Cx, feat, ks, ks, 0)
-    b.fc(feat, Cx, m.fc.out_features, m.fc.weight, m.fc.bias)
+    feat = b.buffer(1, 1, cp(Cx))
+    b.pool(_lib.POOL_AVG, x, cp(Cx), feat, ks, ks, 0)
+    fw = m.fc.weight
+    if cp(Cx) != Cx:
+        fw = torch.zeros(fw.shape[0], cp(Cx), dtype=fw.dtype, device=fw.device)
+        fw[:, :Cx] = m.fc.weight
+    b.fc(feat, cp(Cx), m.fc.out_features, fw, m.fc.bias)
     return Classifier(b, x_in, (3, H, W), m.fc.out_features, precision, max_batch, arch="resnet_cifar")
 
 
