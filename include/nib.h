@@ -300,6 +300,26 @@ int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S,
                 void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Pixel-coordinate GP regression on an inducing grid (KISS-GP / SKI) and its training heat map.
+ * Replaces gp_regression.py:63-104 (heat map from the ./masks PNGs), :160-176 (GPRegressionModel:
+ * ExactGP + GridInterpolationKernel(RBF, grid_size=30) + outputscale) and :244-261 (posterior over
+ * all n x n pixels).  gpytorch is absent and unpinned (pre-0.1 API): parity unpinned; arithmetic
+ * restated from the published SKI construction, see csrc/ski.cu.  The dense G x G algebra
+ * (G = grid_size^2) uses nib_gp_gram_rbf / nib_gp_dgemm_sub / nib_gp_cholesky / nib_gp_trsm.
+ *   nib_heatmap_pixels  d_heat[p] += sum_i d_y[i] * [d_masks[i*P + p] == on_value]   (u8 masks)
+ *   nib_ski_accumulate  A += W^T W [G,G], b += W^T (y - const_mean) [G] over n points d_X [n,2]
+ *                       (cubic-convolution weights on the grid grid0 + k*spacing, k < grid_size)
+ *   nib_ski_predict     mean[q] = const_mean + w_q^T mean_u;  var[q] = noise*|Gm w_q|^2 (+ noise)
+ * ---------------------------------------------------------------------------------------- */
+int nib_heatmap_pixels(const uint8_t* d_masks, const float* d_y, int N, int P, int on_value,
+                       float* d_heat, void* stream);
+int nib_ski_accumulate(const double* d_X, const double* d_y, int n, double grid0, double spacing,
+                       int grid_size, double const_mean, double* d_A, double* d_b, void* stream);
+int nib_ski_predict(const double* d_Xq, int m, double grid0, double spacing, int grid_size,
+                    double const_mean, const double* d_mean_u, const double* d_Gm, double noise,
+                    int add_noise, double* d_mean, double* d_var, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Superpixel label map — HOST function, HOST pointers, no device needed.
  * Replaces `felzenszwalb(img_as_float(img), scale=100, sigma=0.5, min_size=50)`
  * (generate_gp_training_data_imagenet.py:183, generate_gp_training_data_mnist.py:187,

@@ -91,6 +91,9 @@ _PROTOTYPES = {
     "nib_gp_colsumsq": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "nib_gp_append_row": (_i, [_vp, _vp, _d, _vp, _vp, _i, _vp]),
     "nib_heatmap": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "nib_heatmap_pixels": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nib_ski_accumulate": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp, _vp]),
+    "nib_ski_predict": (_i, [_vp, _i, _d, _d, _i, _d, _vp, _vp, _d, _i, _vp, _vp, _vp]),
     "nib_felzenszwalb": (_i, [_vp, _i, _i, _i, _d, _d, _i, _vp, C.POINTER(_i)]),
 }
 
