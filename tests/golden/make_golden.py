@@ -13,6 +13,7 @@ Fixtures
   masks_mnist.npz      generate_gp_training_data_mnist.py     a1 prep, dummy randint + draw, mask, renormalise
   resnet56.npz         models/resnet.py createModel + shipped checkpoint -> logits of a seeded batch
   mnist_net.npz        generate_gp_training_data_mnist.py :72-105 class statements + shipped checkpoint -> 4-tuple
+  utils.npz            utils.normalize_image / utils.generate_IOU executed on seeded inputs
   ei.npz               BayesianOptimization.expected_improvement on fixed (mu, sigma)
   gp_sklearn.npz       scikit-learn 1.9.0 GaussianProcessRegressor as built at BayesianOptimization.py:154-159
 """
@@ -177,6 +178,23 @@ def make_mnist_net():
                         x0_mean=x0.mean((2, 3)).numpy(), x1_mean=x1.mean((2, 3)).numpy(), ref_lines=np.array(span))
 
 
+def make_utils():
+    """utils.py imports cleanly: normalize_image and generate_IOU are executed as they stand.  generate_boundingbox unpacks
+    three values from cv2.findContours (OpenCV 3) and raises under the container's OpenCV 4, so it is not pinned."""
+    import tempfile
+    mod = _load_ref_module("ref_utils", "utils.py")
+    rng = np.random.RandomState(0)
+    img_u8 = rng.randint(0, 256, size=(5, 7, 3)).astype(np.uint8)
+    norm = mod.normalize_image(img_u8)
+    boxes = rng.randint(0, 200, size=(16, 2, 2))
+    A = np.concatenate([boxes[:, 0], boxes[:, 0] + rng.randint(1, 60, size=(16, 2))], 1)
+    B = np.concatenate([boxes[:, 1], boxes[:, 1] + rng.randint(1, 60, size=(16, 2))], 1)
+    canvas = np.zeros((300, 300, 3), np.uint8)
+    with tempfile.TemporaryDirectory() as d, contextlib.redirect_stdout(io.StringIO()):
+        iou = np.array([mod.generate_IOU(list(a), list(b), canvas, k, d) for k, (a, b) in enumerate(zip(A, B))])
+    np.savez_compressed(os.path.join(OUT, "utils.npz"), img_u8=img_u8, norm=norm, boxA=A, boxB=B, iou=iou)
+
+
 def make_ei():
     rel = "BayesianOptimization.py"
     code, span = _extract(rel, "def expected_improvement(", "return -1 * expected_improvement")
@@ -246,6 +264,7 @@ if __name__ == "__main__":
     make_masks_mnist()
     make_resnet56()
     make_mnist_net()
+    make_utils()
     make_ei()
     make_gp_sklearn()
     for f in sorted(os.listdir(OUT)):
