@@ -310,7 +310,8 @@ def run_ours(args):
     roofline = None
     if rank == 0:
         clf.forward_masked(synth, my_bits_dev[:mb], nib.KEEP_MUL, out=logits[:min(mb, per)])
-        prof = [clf.profile(min(mb, per)) for _ in range(3)][-1]
+        profs = sorted((clf.profile(min(mb, per)) for _ in range(5)), key=lambda pr: sum(p[0] for p in pr))
+        prof = profs[len(profs) // 2]     # median of five passes by total time (the GPU sits at its power cap: +-5 %)
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"micro_batch": min(mb, per), "ops": [
@@ -336,6 +337,10 @@ def run_ours(args):
                         "flops_per_launch": tc_fl / n_tc,
                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                         "launches_per_forward": n_tc, "share_of_forward": tc_ms / all_ms if all_ms else None,
+                        # the same flops over (timed-region time x this share): what the conv kernels deliver inside the
+                        # real step, where launches run back to back (PDL, two streams) instead of between event records
+                        "achieved_in_step": (tc_fl * (per / min(mb, per)) * args.steps / ((ms / 1e3) * (tc_ms / all_ms)) / 1e12)
+                        if all_ms else None,
                         "per_kind_ms": {"simt_conv": sum(p[0] for p in prof if p[1] == 0), "tc_conv": tc_ms,
                                         "pool": sum(p[0] for p in prof if p[1] == 2), "fc": sum(p[0] for p in prof if p[1] == 3)}}
         else:
@@ -356,10 +361,11 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.arch == "resnet101" else f"masked forward evals/sec ({args.arch} 224^2)",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "generate_gp_training_data_imagenet.py: ResNet-101 224^2, S=50 superpixels, "
+            "config": {"workload": f"generate_gp_training_data_imagenet.py: {args.arch} 224^2, S=50 superpixels, "
                                    "k=20 keep-masks, mask synthesis + forward + top-1/softmax scoring + score all-gather",
                        "arch": args.arch, "masks_per_step_per_gpu": M, "micro_batch": mb, "streams": args.streams, "sharding": f"masks over {world} ranks",
                        "weights": "random init, seeded (no network for pretrained weights)", "cuda_graph": bool(args.graph),
