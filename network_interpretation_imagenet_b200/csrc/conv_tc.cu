@@ -1287,6 +1287,431 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+
+// =====================================================================================================
+// Fused pair of 1x1 convolutions: a bottleneck's expansion c (K1 -> N1, + residual, ReLU) and the NEXT bottleneck's
+// reduction a (N1 -> N2, ReLU), one kernel.  Run separately, the N1-channel tensor y is written by c and read back by a
+// (103 MB per launch at micro-batch 256 in layer 3, the largest single stream of bytes in the network); here each
+// 128-column chunk of y is converted to bf16 in shared memory once, TMA-stored to global (the next block's residual
+// still needs it) AND consumed in place as the A operand of the second GEMM — the epilogue's swizzled 128 x 64 boxes are
+// exactly a K-major SWIZZLE_128B UMMA operand.
+//
+//   per CTA pair and 256-row tile:   for chunk j of N1/128:
+//     MMA1(j):  acc1[j&1] (128 TMEM columns, double buffered) = h[256 x K1] * Wc[chunk j]^T        (ring 1: A1 + B1)
+//     EPI1(j):  + bias + residual (TMA-loaded into the staging set, added in place) -> ReLU -> bf16 staging set j&1
+//               -> TMA store of y;  signals y_ready
+//     MMA2(j):  acc2 (N2 columns) += y_chunk[256 x 128] * Wa[:, chunk j]^T                         (ring 2: B2)
+//   EPI2: acc2 + bias -> ReLU -> bf16 -> (the warpgroup's own staging set) -> TMA store.
+// TMEM: 2 x 128 + N2 <= 512 columns.  Warp roles as in conv_tc3_kernel; warpgroup g of the epilogue owns the chunks of
+// parity g, TMEM buffer g and staging set g, and half of the N2 output columns.
+struct TcFusedParams {
+  const float* bias1;
+  const float* bias2;
+  const __nv_bfloat16* res;   // residual [M][N1], compact
+  int M, m_tiles;
+  int kb1;      // K1 / 64
+  int nch;      // N1 / 128 (even)
+  int n1;
+  int relu1, relu2;
+  unsigned int* err_flag;
+  unsigned long long* dbg;   // NIB_TC_DBG=1: per-CTA wait timers (cycles), 32 slots per CTA; null in production
+};
+
+template <int N2>
+struct TcFusedSmem {
+  static constexpr int S1 = 4, S2 = 4;                               // one chunk of B1, two chunks of B2
+  static constexpr int A1_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;       // 16 KB per K block
+  static constexpr int A1_KB = 4;                                    // K1 <= 256: the tile's whole A operand stays resident
+  static constexpr int B1_BYTES = 64 * TC_BLOCK_K * 2;               // this CTA's 64 of the chunk's 128 weight rows
+  static constexpr int B2_BYTES = (N2 / 2) * TC_BLOCK_K * 2;         // this CTA's half of Wa's rows, one K block
+  static constexpr int BOX_BYTES = TC_BLOCK_M * 128;                 // 128 rows x 64 channels bf16
+  static constexpr int R1_OFFSET = A1_KB * A1_BYTES;                 // ring 1: B1 only
+  static constexpr int R2_OFFSET = R1_OFFSET + S1 * B1_BYTES;
+  static constexpr int STG_OFFSET = R2_OFFSET + S2 * B2_BYTES;       // [set 2][box 2] x 16 KB
+  static constexpr int BIAS1_OFFSET = STG_OFFSET + 4 * BOX_BYTES;    // [warpgroup][128] floats: the current chunk's bias
+  static constexpr int BIAS2_OFFSET = BIAS1_OFFSET + 2 * 128 * 4;
+  static constexpr int BAR_OFFSET = BIAS2_OFFSET + N2 * 4;
+  static constexpr int NUM_BARS = 2 * S1 + 2 * S2 + 14;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
+  static constexpr int EP2_WARPS = N2 >= 128 ? 8 : 4;                // epilogue warps per CTA that drain acc2
+};
+
+template <int N2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                     const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmY,
+                     const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut2,
+                     const TcFusedParams p) {
+  using SM = TcFusedSmem<N2>;
+  constexpr int S1 = SM::S1, S2 = SM::S2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) {
+    if (threadIdx.x == 0 && p.err_flag) atomicExch(p.err_flag, 9u);
+    __trap();
+  }
+  const uint32_t bar_base = smem_base + SM::BAR_OFFSET;
+  auto full1 = [&](int s) { return bar_base + 8u * s; };                       // leader
+  auto empty1 = [&](int s) { return bar_base + 8u * (S1 + s); };
+  auto full2 = [&](int s) { return bar_base + 8u * (2 * S1 + s); };            // leader
+  auto empty2 = [&](int s) { return bar_base + 8u * (2 * S1 + S2 + s); };
+  const uint32_t bar2 = bar_base + 8u * (2 * S1 + 2 * S2);
+  auto acc1_full = [&](int b) { return bar2 + 8u * b; };
+  auto acc1_empty = [&](int b) { return bar2 + 8u * (2 + b); };                // leader
+  auto res_full = [&](int b) { return bar2 + 8u * (4 + b); };
+  auto y_ready = [&](int b) { return bar2 + 8u * (6 + b); };                   // leader
+  auto stage_free = [&](int b) { return bar2 + 8u * (8 + b); };
+  const uint32_t acc2_full = bar2 + 8u * 10;
+  const uint32_t acc2_empty = bar2 + 8u * 11;                                  // leader
+  const uint32_t a1_full = bar2 + 8u * 12;                                     // leader
+  const uint32_t a1_empty = bar2 + 8u * 13;
+  const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  auto stg = [&](int set, int box) { return smem_base + SM::STG_OFFSET + (uint32_t)(set * 2 + box) * SM::BOX_BYTES; };
+  float* bias1_s = reinterpret_cast<float*>(smem_raw + SM::BIAS1_OFFSET);
+  float* bias2_s = reinterpret_cast<float*>(smem_raw + SM::BIAS2_OFFSET);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t ACC2_COL = 256;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA1); prefetch_tmap(&tmB1); prefetch_tmap(&tmRes);
+    prefetch_tmap(&tmY); prefetch_tmap(&tmB2); prefetch_tmap(&tmOut2);
+    for (int s = 0; s < S1; ++s) { mbar_init(full1(s), 1); mbar_init(empty1(s), 1); }
+    for (int s = 0; s < S2; ++s) { mbar_init(full2(s), 1); mbar_init(empty2(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc1_full(b), 1);
+      mbar_init(acc1_empty(b), 8);     // 4 warps of warpgroup b in each CTA
+      mbar_init(res_full(b), 1);
+      mbar_init(y_ready(b), 8);
+      mbar_init(stage_free(b), 5);     // MMA2 commit + the 4 warps whose stores read the set
+    }
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 2 * SM::EP2_WARPS);
+    mbar_init(a1_full, 1);
+    mbar_init(a1_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  // biases are weights: safe to read before the previous layer has finished
+  for (int i = threadIdx.x; i < N2; i += blockDim.x) bias2_s[i] = p.bias2 ? p.bias2[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool dbg_on = p.dbg != nullptr;
+  long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_role0 = clock64();
+#define FT(slot, stmt)                                                                      \
+  do {                                                                                      \
+    if (dbg_on) { const long long _t = clock64(); stmt; t_acc[slot] += clock64() - _t; }    \
+    else { stmt; }                                                                          \
+  } while (0)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    int s1 = 0, s2 = 0;
+    uint32_t ph1 = 0, ph2 = 0;
+    const uint32_t lfull1 = mapa_shared(full1(0), 0), lfull2 = mapa_shared(full2(0), 0);
+    const uint32_t la1_full = mapa_shared(a1_full, 0);
+    int it = 0;
+    for (int tile = pair; tile < m_pairs; tile += npairs, ++it) {
+      const int m0 = (tile * 2 + (int)rank) * TC_BLOCK_M;
+      // the tile's A operand (128 rows x K1) is loaded once and reused by every chunk: re-streaming it per chunk made A
+      // 40 % of all bytes the SM had to receive, and the kernel is bound by exactly that
+      FT(0, mbar_wait(a1_empty, ((uint32_t)it & 1u) ^ 1u, p.err_flag, 32));
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(a1_full, (uint32_t)(2 * p.kb1 * SM::A1_BYTES));
+        for (int kb = 0; kb < p.kb1; ++kb)
+          tma2_load_2d(smem_base + (uint32_t)kb * SM::A1_BYTES, &tmA1, la1_full, kb * TC_BLOCK_K, m0);
+      }
+      __syncwarp();
+      // issue order = consumption order of the MMA warp: MMA1(0), MMA1(1), MMA2(0), MMA1(2), MMA2(1), ...  (with B2 of chunk
+      // j ahead of B1 of chunk j+1 the producer sat in the ring-2 wait while MMA1 starved: 60 % of the kernel time)
+      auto issue_b1 = [&](int j) {
+        for (int kb = 0; kb < p.kb1; ++kb) {
+          FT(1, mbar_wait(empty1(s1), ph1 ^ 1u, p.err_flag, 22));
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(full1(s1), (uint32_t)(2 * SM::B1_BYTES));
+            tma2_load_2d(smem_base + SM::R1_OFFSET + (uint32_t)s1 * SM::B1_BYTES, &tmB1, lfull1 + 8u * s1, kb * TC_BLOCK_K,
+                         j * 128 + (int)rank * 64);
+          }
+          __syncwarp();
+          if (++s1 == S1) { s1 = 0; ph1 ^= 1u; }
+        }
+      };
+      auto issue_b2 = [&](int j) {
+        for (int kk = 0; kk < 2; ++kk) {
+          FT(2, mbar_wait(empty2(s2), ph2 ^ 1u, p.err_flag, 23));
+          if (elect_one()) {
+            const uint32_t dst = smem_base + SM::R2_OFFSET + (uint32_t)s2 * SM::B2_BYTES;
+            if (rank == 0) mbar_arrive_expect_tx(full2(s2), (uint32_t)(2 * SM::B2_BYTES));
+            tma2_load_2d(dst, &tmB2, lfull2 + 8u * s2, j * 128 + kk * TC_BLOCK_K, (int)rank * (N2 / 2));
+          }
+          __syncwarp();
+          if (++s2 == S2) { s2 = 0; ph2 ^= 1u; }
+        }
+      };
+      issue_b1(0);
+      for (int j = 0; j < p.nch; ++j) {
+        if (j + 1 < p.nch) issue_b1(j + 1);
+        issue_b2(j);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc1 = make_idesc_bf16_pair<128>();
+      constexpr uint32_t idesc2 = make_idesc_bf16_pair<N2>();
+      int s1 = 0, s2 = 0;
+      uint32_t ph1 = 0, ph2 = 0;
+      int it = 0;
+      for (int tile = pair; tile < m_pairs; tile += npairs, ++it) {
+        for (int j = 0; j <= p.nch; ++j) {
+          if (j < p.nch) {
+            const int b = j & 1;
+            const uint32_t use = (uint32_t)((it * p.nch + j) >> 1);
+            FT(0, mbar_wait(acc1_empty(b), (use & 1u) ^ 1u, p.err_flag, 24));
+            if (j == 0) FT(1, mbar_wait(a1_full, (uint32_t)it & 1u, p.err_flag, 33));
+            tc_fence_after();
+            const uint32_t d1 = tmem_base + (uint32_t)(b * 128);
+            for (int kb = 0; kb < p.kb1; ++kb) {
+              FT(2, mbar_wait(full1(s1), ph1, p.err_flag, 25));
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t adesc = make_smem_desc_sw128(smem_base + (uint32_t)kb * SM::A1_BYTES);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_base + SM::R1_OFFSET + (uint32_t)s1 * SM::B1_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+                  umma2_bf16(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb | k) != 0);
+                umma2_commit_both(empty1(s1));
+                if (kb == p.kb1 - 1) {
+                  umma2_commit_both(acc1_full(b));
+                  if (j == p.nch - 1) umma2_commit_both(a1_empty);     // the next tile's A may land
+                }
+              }
+              __syncwarp();
+              if (++s1 == S1) { s1 = 0; ph1 ^= 1u; }
+            }
+          }
+          if (j >= 1) {
+            const int jj = j - 1, b = jj & 1;
+            const uint32_t use = (uint32_t)((it * p.nch + jj) >> 1);
+            FT(3, mbar_wait(y_ready(b), use & 1u, p.err_flag, 26));
+            if (jj == 0) FT(4, mbar_wait(acc2_empty, ((uint32_t)it & 1u) ^ 1u, p.err_flag, 27));
+            tc_fence_after();
+            const uint32_t d2 = tmem_base + ACC2_COL;
+            for (int kk = 0; kk < 2; ++kk) {
+              FT(5, mbar_wait(full2(s2), ph2, p.err_flag, 28));
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t adesc = make_smem_desc_sw128(stg(b, kk));
+                const uint64_t bdesc = make_smem_desc_sw128(smem_base + SM::R2_OFFSET + (uint32_t)s2 * SM::B2_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+                  umma2_bf16(d2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (jj | kk | k) != 0);
+                umma2_commit_both(empty2(s2));
+                if (kk == 1) {
+                  umma2_commit_both(stage_free(b));
+                  if (jj == p.nch - 1) umma2_commit_both(acc2_full);
+                }
+              }
+              __syncwarp();
+              if (++s2 == S2) { s2 = 0; ph2 ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warpgroup g = chunks of parity g, TMEM buffer g, staging set g =====
+    const int ew = warp - 2;
+    const int g = ew >> 2;
+    const int quarter = warp & 3;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const uint32_t lead_acc1_empty = mapa_shared(acc1_empty(g), 0);
+    const uint32_t lead_y_ready = mapa_shared(y_ready(g), 0);
+    const uint32_t lead_acc2_empty = mapa_shared(acc2_empty, 0);
+    const uint32_t relu1_floor = p.relu1 ? 0u : 0xFF80FF80u;
+    const uint32_t relu2_floor = p.relu2 ? 0u : 0xFF80FF80u;
+    constexpr bool EP2_ALL = N2 >= 128;
+    const bool ep2 = EP2_ALL || g == 0;
+    constexpr int UN2 = N2 >= 128 ? N2 / 128 : 1;        // 64-column boxes of acc2 per participating warpgroup
+    const int col2_base = EP2_ALL ? g * (N2 / 2) : 0;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // The warpgroup fetches its own residual chunks: one lane waits until the staging set is free again (its four warps'
+    // stores have read it and MMA2 has consumed it) and issues the TMA load for the warpgroup's next chunk right there
+    // (with the loads on the producer warp, its operand rings stalled behind every such wait).  The residual is added in
+    // place in the staging set, as in conv_tc3; fetching it global -> registers instead was measured slower (the loads'
+    // latency lands inside the epilogue math: 131 vs 114 kcycles per launch at the layer-3 shape).
+    auto fetch_residual = [&](uint32_t use_next, int j_next, int m0_next) {
+      if (quarter == 0 && lane == 0) {
+        FT(0, mbar_wait(stage_free(g), (use_next & 1u) ^ 1u, p.err_flag, 21));
+        mbar_arrive_expect_tx(res_full(g), (uint32_t)(2 * SM::BOX_BYTES));
+        tma_load_2d(stg(g, 0), &tmRes, res_full(g), j_next * 128, m0_next);
+        tma_load_2d(stg(g, 1), &tmRes, res_full(g), j_next * 128 + 64, m0_next);
+        if (j_next + 2 < p.nch) {   // the chunk after that one: have it in L2 by the time its load is issued
+          tma_prefetch_2d(&tmRes, (j_next + 2) * 128, m0_next);
+          tma_prefetch_2d(&tmRes, (j_next + 2) * 128 + 64, m0_next);
+        }
+      }
+      __syncwarp();
+    };
+    const int wt = (int)threadIdx.x - 64 - g * 128;                // 0..127 inside the warpgroup
+    float* bias1_wg = bias1_s + g * 128;
+    if (pair < m_pairs) fetch_residual(0u, g, (pair * 2 + (int)rank) * TC_BLOCK_M);
+    int it = 0;
+    for (int tile = pair; tile < m_pairs; tile += npairs, ++it) {
+      const int m0 = (tile * 2 + (int)rank) * TC_BLOCK_M;
+      const bool more_tiles = tile + npairs < m_pairs;
+      const int m0_next = ((tile + npairs) * 2 + (int)rank) * TC_BLOCK_M;
+      for (int j = g; j < p.nch; j += 2) {
+        const uint32_t use = (uint32_t)((it * p.nch + j) >> 1);
+        // this chunk's 128 bias values: one per thread into the warpgroup's window (the previous chunk's readers are past
+        // the named barrier of their own chunk; the barrier below orders this write against them and publishes it)
+        const float bias_reg = p.bias1 ? __ldg(p.bias1 + j * 128 + wt) : 0.f;
+        named_bar_sync(1 + g, 128);
+        bias1_wg[wt] = bias_reg;
+        named_bar_sync(1 + g, 128);
+        FT(1, mbar_wait(res_full(g), use & 1u, p.err_flag, 29));
+        FT(2, mbar_wait(acc1_full(g), use & 1u, p.err_flag, 30));
+        tc_fence_after();
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t slab = stg(g, b) + (uint32_t)(quarter * 4096);
+          const uint32_t obase = slab + (uint32_t)lane * 128u;
+          uint32_t v[64];
+          __syncwarp();
+          tmem_ld_32x32b_x64(lane_taddr + (uint32_t)(g * 128 + b * 64), v);
+          tmem_ld_wait();
+          if (b == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(lead_acc1_empty);
+          }
+          const float* bsrc = bias1_wg + b * 64;
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint64_t a0 = pack_f32x2(v[c * 8 + 0], v[c * 8 + 1]), a1 = pack_f32x2(v[c * 8 + 2], v[c * 8 + 3]);
+            uint64_t a2 = pack_f32x2(v[c * 8 + 4], v[c * 8 + 5]), a3 = pack_f32x2(v[c * 8 + 6], v[c * 8 + 7]);
+            const float4 b0 = *reinterpret_cast<const float4*>(bsrc + c * 8), b1 = *reinterpret_cast<const float4*>(bsrc + c * 8 + 4);
+            a0 = add_f32x2(a0, pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)));
+            a1 = add_f32x2(a1, pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)));
+            a2 = add_f32x2(a2, pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)));
+            a3 = add_f32x2(a3, pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w)));
+            const uint4 r = lds_v4(obase + ((((uint32_t)c) ^ sw) << 4));   // 8 bf16 residual values of this row
+            a0 = add_f32x2(a0, pack_f32x2(r.x << 16, r.x & 0xFFFF0000u)); a1 = add_f32x2(a1, pack_f32x2(r.y << 16, r.y & 0xFFFF0000u));
+            a2 = add_f32x2(a2, pack_f32x2(r.z << 16, r.z & 0xFFFF0000u)); a3 = add_f32x2(a3, pack_f32x2(r.w << 16, r.w & 0xFFFF0000u));
+            o[c * 4 + 0] = max_bf16x2(cvt_bf16x2(a0), relu1_floor); o[c * 4 + 1] = max_bf16x2(cvt_bf16x2(a1), relu1_floor);
+            o[c * 4 + 2] = max_bf16x2(cvt_bf16x2(a2), relu1_floor); o[c * 4 + 3] = max_bf16x2(cvt_bf16x2(a3), relu1_floor);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts_v4(obase + ((((uint32_t)c) ^ sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
+          fence_async_smem();   // generic-proxy writes -> visible to the TMA store and to tcgen05.mma (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmY, slab, j * 128 + b * 64, m0 + quarter * 32);
+            bulk_commit();
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_y_ready);      // release at cluster scope: the leader's MMA reads this CTA's set
+        const bool defer = ep2 && (j + 2 >= p.nch);            // the set is reused by EPI2 before it goes back to the producer
+        if (!defer) {
+          if (lane == 0) {
+            bulk_wait_read<0>();
+            mbar_arrive(stage_free(g));
+          }
+          __syncwarp();
+          if (j + 2 < p.nch) fetch_residual(use + 1u, j + 2, m0);
+          else if (more_tiles) fetch_residual(use + 1u, g, m0_next);
+        }
+      }
+      if (ep2) {
+        FT(3, mbar_wait(acc2_full, (uint32_t)it & 1u, p.err_flag, 31));
+        tc_fence_after();
+        if (lane == 0) bulk_wait_read<0>();     // the y stores of this warp's last chunk have read the set
+        __syncwarp();
+#pragma unroll 1
+        for (int u = 0; u < UN2; ++u) {
+          const int col2 = col2_base + u * 64;
+          const uint32_t slab = stg(g, u) + (uint32_t)(quarter * 4096);
+          const uint32_t obase = slab + (uint32_t)lane * 128u;
+          uint32_t v[64];
+          __syncwarp();
+          tmem_ld_32x32b_x64(lane_taddr + ACC2_COL + (uint32_t)col2, v);
+          tmem_ld_wait();
+          if (u == UN2 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(lead_acc2_empty);
+          }
+          const float* bsrc = bias2_s + col2;
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint64_t a0 = pack_f32x2(v[c * 8 + 0], v[c * 8 + 1]), a1 = pack_f32x2(v[c * 8 + 2], v[c * 8 + 3]);
+            uint64_t a2 = pack_f32x2(v[c * 8 + 4], v[c * 8 + 5]), a3 = pack_f32x2(v[c * 8 + 6], v[c * 8 + 7]);
+            const float4 b0 = *reinterpret_cast<const float4*>(bsrc + c * 8), b1 = *reinterpret_cast<const float4*>(bsrc + c * 8 + 4);
+            a0 = add_f32x2(a0, pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)));
+            a1 = add_f32x2(a1, pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)));
+            a2 = add_f32x2(a2, pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)));
+            a3 = add_f32x2(a3, pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w)));
+            o[c * 4 + 0] = max_bf16x2(cvt_bf16x2(a0), relu2_floor); o[c * 4 + 1] = max_bf16x2(cvt_bf16x2(a1), relu2_floor);
+            o[c * 4 + 2] = max_bf16x2(cvt_bf16x2(a2), relu2_floor); o[c * 4 + 3] = max_bf16x2(cvt_bf16x2(a3), relu2_floor);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts_v4(obase + ((((uint32_t)c) ^ sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut2, slab, col2, m0 + quarter * 32);
+            bulk_commit();
+          }
+        }
+        if (lane == 0) {
+          bulk_wait_read<0>();
+          mbar_arrive(stage_free(g));
+        }
+        __syncwarp();
+        if (more_tiles) fetch_residual((uint32_t)(((it + 1) * p.nch + g) >> 1), g, m0_next);
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    tc_fence_before();
+  }
+#undef FT
+  if (dbg_on && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8)) {
+    // slots: producer 0-7, MMA 8-15, epilogue warpgroup 0 (its residual-issuing warp) 16-23, warpgroup 1 24-31;
+    // entry 7 of each = the role's whole time
+    const int role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : 3;
+    unsigned long long* d = p.dbg + (size_t)blockIdx.x * 32 + role * 8;
+    for (int i = 0; i < 7; ++i) d[i] = (unsigned long long)t_acc[i];
+    d[7] = (unsigned long long)(clock64() - t_role0);
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1571,6 +1996,143 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
 }
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+
+// ---- fused expansion + next reduction (conv_fused_ca_kernel) ------------------------------------------------
+struct TcFusedPlan {
+  CUtensorMap tmA1, tmB1, tmRes, tmY, tmB2, tmOut2;
+  int n2;
+  unsigned int* err_flag;
+};
+
+static bool compact_1x1(const ConvParams& p) {
+  return p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.in_cstride == p.Cin && p.in_coff == 0 &&
+         p.out_cstride == p.Cout && p.out_coff == 0 && p.in_halo == 0 && p.out_halo == 0 && p.pre_scale == nullptr;
+}
+
+// c: 1x1 K1 -> N1 with a full-width residual; a: 1x1 N1 -> N2 reading exactly c's output.  NIB_TC_FUSE=0 disables.
+bool tc_fuse_supported(const ConvParams& c, const ConvParams& a) {
+  const char* e = getenv("NIB_TC_FUSE");
+  if (e != nullptr && atoi(e) == 0) return false;
+  if (tc_version() < 3) return false;
+  if (!compact_1x1(c) || !compact_1x1(a)) return false;
+  if (c.res == nullptr || c.res_C != c.Cout || c.res_cstride != c.Cout || c.res_coff != 0) return false;
+  if (c.Cin % TC_BLOCK_K != 0 || c.Cin > 256 || c.Cout % 256 != 0 || c.Cout > 1024) return false;
+  if (a.in != c.out || a.Cin != c.Cout || a.res != nullptr) return false;
+  if (a.Cout != 64 && a.Cout != 128 && a.Cout != 256) return false;
+  if (a.P != c.P || a.Q != c.Q || a.M != c.M) return false;
+  return true;
+}
+
+int tc_fused_plan_create(const ConvParams& c, const ConvParams& a, int max_batch, TcFusedPlan** out) {
+  int rc = load_driver_fns();
+  if (rc != NIB_OK) return rc;
+  if (!g_err_flag) {
+    NIB_CUDA(cudaMalloc(&g_err_flag, sizeof(unsigned int)));
+    NIB_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
+  }
+  TcFusedPlan* plan = new TcFusedPlan();
+  memset(plan, 0, sizeof(*plan));
+  plan->err_flag = g_err_flag;
+  plan->n2 = a.Cout;
+  const uint64_t rows = (uint64_t)max_batch * c.P * c.Q;
+  const uint64_t K1 = (uint64_t)c.Cin, N1 = (uint64_t)c.Cout, N2 = (uint64_t)a.Cout;
+  rc = encode_2d_bf16(&plan->tmA1, c.in, K1, rows, K1 * 2, TC_BLOCK_K, TC_BLOCK_M);
+  if (rc == NIB_OK) rc = encode_2d_bf16(&plan->tmB1, c.w, K1, N1, K1 * 2, TC_BLOCK_K, 64);
+  if (rc == NIB_OK) rc = encode_2d_bf16(&plan->tmRes, c.res, N1, rows, N1 * 2, 64, TC_BLOCK_M);
+  if (rc == NIB_OK) rc = encode_2d_bf16(&plan->tmY, c.out, N1, rows, N1 * 2, 64, 32);
+  if (rc == NIB_OK) rc = encode_2d_bf16(&plan->tmB2, a.w, N1, N2, N1 * 2, TC_BLOCK_K, (uint32_t)(N2 / 2));
+  if (rc == NIB_OK) rc = encode_2d_bf16(&plan->tmOut2, a.out, N2, rows, N2 * 2, 64, 32);
+  if (rc != NIB_OK) { delete plan; return rc; }
+  *out = plan;
+  return NIB_OK;
+}
+
+void tc_fused_plan_destroy(TcFusedPlan* plan) { delete plan; }
+
+template <int N2>
+static int launch_fused(const TcFusedPlan* plan, const TcFusedParams& kp, cudaStream_t st) {
+  using SM = TcFusedSmem<N2>;
+  static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NIB_CUDA(cudaFuncSetAttribute(conv_fused_ca_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  const int m_pairs = (kp.m_tiles + 1) / 2;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = m_pairs < max_pairs ? m_pairs : max_pairs;
+  static const bool pdl = getenv("NIB_TC_NO_PDL") == nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(TC3_THREADS);
+  cfg.dynamicSmemBytes = SM::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
+  NIB_CUDA(cudaLaunchKernelEx(&cfg, conv_fused_ca_kernel<N2>, plan->tmA1, plan->tmB1, plan->tmRes, plan->tmY, plan->tmB2,
+                              plan->tmOut2, kp));
+  return NIB_OK;
+}
+
+int tc_fused_launch(const TcFusedPlan* plan, const ConvParams& c, const ConvParams& a, cudaStream_t st) {
+  TcFusedParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.bias1 = c.bias;
+  kp.bias2 = a.bias;
+  kp.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
+  kp.M = c.M;
+  kp.m_tiles = ceil_div(c.M, TC_BLOCK_M);
+  kp.kb1 = c.Cin / TC_BLOCK_K;
+  kp.nch = c.Cout / 128;
+  kp.n1 = c.Cout;
+  kp.relu1 = c.relu;
+  kp.relu2 = a.relu;
+  kp.err_flag = plan->err_flag;
+  static const bool dbg = getenv("NIB_TC_DBG") != nullptr;
+  if (dbg) {
+    const int nblk = num_sms();
+    unsigned long long* d = nullptr;
+    NIB_CUDA(cudaMalloc(&d, (size_t)nblk * 32 * 8));
+    NIB_CUDA(cudaMemsetAsync(d, 0, (size_t)nblk * 32 * 8, st));
+    kp.dbg = d;
+    int rc = plan->n2 == 64 ? launch_fused<64>(plan, kp, st) : plan->n2 == 128 ? launch_fused<128>(plan, kp, st)
+                                                                                : launch_fused<256>(plan, kp, st);
+    if (rc != NIB_OK) return rc;
+    NIB_CUDA(cudaStreamSynchronize(st));
+    unsigned long long* h = (unsigned long long*)malloc((size_t)nblk * 32 * 8);
+    NIB_CUDA(cudaMemcpy(h, d, (size_t)nblk * 32 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    double avg[32] = {0};
+    int n = 0;
+    for (int b = 0; b < nblk; b += 2) {   // leader CTAs
+      for (int i = 0; i < 32; ++i) avg[i] += (double)h[(size_t)b * 32 + i];
+      ++n;
+    }
+    fprintf(stderr, "[fused K1=%d N1=%d N2=%d M=%d] leader-CTA averages (kcycles)\n", c.Cin, c.Cout, a.Cout, c.M);
+    const char* names[4] = {"producer: a1_empty empty1 empty2 - - - - | total", "mma: acc1_empty a1_full full1 y_ready acc2_empty full2 - | total",
+                            "epi wg0: stage_free res_full acc1_full acc2_full - - - | total", "epi wg1: stage_free res_full acc1_full acc2_full - - - | total"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "  %s\n   ", names[r]);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.1f", avg[r * 8 + i] / n / 1e3);
+      fprintf(stderr, "\n");
+    }
+    free(h);
+    return NIB_OK;
+  }
+  switch (plan->n2) {
+    case 64: return launch_fused<64>(plan, kp, st);
+    case 128: return launch_fused<128>(plan, kp, st);
+    case 256: return launch_fused<256>(plan, kp, st);
+  }
+  set_error("tc_fused_launch: unsupported N2=%d", plan->n2);
+  return NIB_EINVAL;
+}
 int tc_conv_plan_block_n(const TcConvPlan* plan) { return plan->block_n; }
 
 template <int BLOCK_N, int STAGES>

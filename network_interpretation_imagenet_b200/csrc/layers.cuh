@@ -55,4 +55,11 @@ int tc_conv_plan_block_n(const TcConvPlan* plan);
 // launch for a batch with M = N*P*Q valid rows (p.M)
 int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st);
 
+// a bottleneck's 1x1 expansion (+ residual, ReLU) fused with the next bottleneck's 1x1 reduction (conv_fused_ca_kernel)
+struct TcFusedPlan;
+bool tc_fuse_supported(const ConvParams& c, const ConvParams& a);
+int tc_fused_plan_create(const ConvParams& c, const ConvParams& a, int max_batch, TcFusedPlan** out);
+void tc_fused_plan_destroy(TcFusedPlan* plan);
+int tc_fused_launch(const TcFusedPlan* plan, const ConvParams& c, const ConvParams& a, cudaStream_t st);
+
 }  // namespace nib

@@ -30,6 +30,13 @@ struct NetOp {
   void* d_w_pack;     // pre-activation convs in bf16 nets: KRSC weights with Cin zero-padded to a multiple of 64
   int pack_cin;       // that padded Cin (0: no packed tensor-core path for this op)
   TcConvPlan* plan;
+  // 1x1 expansion fused with the next op (the following bottleneck's 1x1 reduction): this op launches both, the next op
+  // carries fused_skip.  next_* is a copy of what the launch needs from that op (the profiler runs ops one at a time).
+  TcFusedPlan* fplan;
+  bool fused_skip;
+  nib_conv_desc next_cd;
+  void* next_w;
+  float* next_bias;
   // pool
   int pool_kind, k, stride, pad, C, in_buf, in_coff, out_buf, out_coff;
   // fc
@@ -120,6 +127,7 @@ int nib_net_destroy(nib_net* net) {
     if (o.d_pre_scale) cudaFree(o.d_pre_scale);
     if (o.d_pre_shift) cudaFree(o.d_pre_shift);
     if (o.plan) tc_conv_plan_destroy(o.plan);
+    if (o.fplan) tc_fused_plan_destroy(o.fplan);
   }
   delete net;
   return NIB_OK;
@@ -358,6 +366,23 @@ int nib_net_finalize(nib_net* net) {
       }
     }
   }
+  if (net->bf16) {
+    for (size_t i = 0; i + 1 < net->ops.size(); ++i) {
+      NetOp& c = net->ops[i];
+      NetOp& a = net->ops[i + 1];
+      if (c.kind != 0 || a.kind != 0 || !c.plan || !a.plan || c.pack_cin || a.pack_cin || c.fused_skip) continue;
+      ConvParams pc, pa;
+      fill_conv_params(net, c, net->max_batch, &pc);
+      fill_conv_params(net, a, net->max_batch, &pa);
+      if (!tc_fuse_supported(pc, pa)) continue;
+      int rc = tc_fused_plan_create(pc, pa, net->max_batch, &c.fplan);
+      if (rc != NIB_OK) return rc;
+      c.next_cd = a.cd;
+      c.next_w = a.d_w;
+      c.next_bias = a.d_bias;
+      a.fused_skip = true;
+    }
+  }
   net->finalized = true;
   return NIB_OK;
 }
@@ -365,10 +390,20 @@ int nib_net_finalize(nib_net* net) {
 static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
   for (auto& op : net->ops) {
     if (op.kind == 0) {
+      if (op.fused_skip && net->use_tc) continue;     // computed by the previous op's fused launch
       ConvParams p;
       fill_conv_params(net, op, N, &p);
       int rc;
-      if (op.plan && net->use_tc && op.pack_cin) {
+      if (op.fplan && net->use_tc) {
+        NetOp nx = op;                                // the fused partner's geometry, weights and bias
+        nx.cd = op.next_cd;
+        nx.d_w = op.next_w;
+        nx.d_bias = op.next_bias;
+        ConvParams pa;
+        fill_conv_params(net, nx, N, &pa);
+        rc = tc_fused_launch(op.fplan, p, pa, st);
+        net->tc_launches++;
+      } else if (op.plan && net->use_tc && op.pack_cin) {
         const NetBuffer& bi = net->bufs[op.cd.in_buf];
         rc = launch_bnrelu_pack(bi.ptr, bi.C, op.cd.in_coff, op.cd.Cin, op.pack_cin, op.d_pre_scale, op.d_pre_shift,
                                 net->pack_scratch, (long long)N * bi.H * bi.W, st);
