@@ -330,7 +330,7 @@ def run_ours(args):
             traffic, n_cap = ncu_traffic_per_launch()
             if traffic is not None and min(mb, per) != 256:
                 traffic = traffic * min(mb, per) / 256.0    # the capture was taken at micro-batch 256
-            roofline = {"bound": "tensor", "kernel": "conv_tc3_kernel (tcgen05 cta_group::2 implicit GEMM)", "achieved": ach,
+            roofline = {"bound": "tensor", "kernel": "conv_tc3_kernel + conv_fused_ca_kernel (tcgen05 cta_group::2 implicit GEMM)", "achieved": ach,
                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
                         "traffic_source": "profiles/r01_ncu_all_launches_one_forward_v3_mb256.csv: mean DRAM bytes per conv "
@@ -369,7 +369,8 @@ def run_ours(args):
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"generate_gp_training_data_imagenet.py: {args.arch} 224^2, S=50 superpixels, "
                                    "k=20 keep-masks, mask synthesis + forward + top-1/softmax scoring + score all-gather",
-                       "arch": args.arch, "masks_per_step_per_gpu": M, "micro_batch": mb, "streams": args.streams, "sharding": f"masks over {world} ranks",
+                       "arch": args.arch, "masks_per_step_per_gpu": M, "micro_batch": mb, "streams": args.streams,
+                       "fused_expand_reduce": os.environ.get("NIB_TC_FUSE", "1") != "0", "sharding": f"masks over {world} ranks",
                        "weights": "random init, seeded (no network for pretrained weights)", "cuda_graph": bool(args.graph),
                        "l2": "no explicit flush: each step streams > 10 GB of activations through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
