@@ -942,23 +942,6 @@ gemv_mean_kernel(const double* __restrict__ Ks, int m, int n, int ldks, const do
   if (lane == 0) mu[q] = y_std * acc + y_mean;
 }
 
-__global__ void __launch_bounds__(256)
-colsumsq_var_kernel(const double* __restrict__ V, int n, int m, double prior_var, double y_std, double* __restrict__ var,
-                    double* __restrict__ sd) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= m) return;
-  double acc = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const double v = V[(size_t)i * m + q];
-    acc = fma(v, v, acc);
-  }
-  double r = prior_var - acc;
-  if (r < 0.0) r = 0.0;  // _gpr.py:485-492
-  r = r * y_std * y_std;
-  if (var) var[q] = r;
-  if (sd) sd[q] = sqrt(r);
-}
-
 // ---- column reductions over V [n][m] (row-major): one pass over HBM, rows split into slices so the grid fills the GPU --
 // mode 0: partial[s][j] = sum_t x[t] * V[t][j];  mode 1: partial[s][j] = sum_t V[t][j]^2   (t in slice s)
 static constexpr int CR_ROWS = 64;   // rows per slice
