@@ -913,6 +913,64 @@ static int chol_rec(double* Kx, int ld, int k0, int w, double* dinv, int* info, 
   return chol_rec(Kx, ld, k0 + wa, wb, dinv, info, st);
 }
 
+// Right-looking Cholesky with one step of lookahead.  The diagonal-block factorisation (+ inverse) is a one-block kernel
+// of ~44 us whose 64 pivots form an unavoidable dependent chain; 128 of them were 5.7 of the 16.4 ms of an n = 8192
+// factorisation.  Each update (rank 64 inside a super-block, rank NBC behind it) is therefore split in three: the next
+// diagonal block first, then — while a second stream already factors that block — the column block below it and the
+// rest.  The main stream only waits for the factorisation when it needs the inverse for the next panel product.
+static cudaStream_t g_chol_side = nullptr;
+static cudaEvent_t g_chol_ev_diag = nullptr, g_chol_ev_potrf = nullptr;
+
+static int syrk_part(double* Kx, int ld, int r0, int M, int cc0, int N, int c0, int Kd, int lower_only, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || Kd <= 0) return NIB_OK;
+  DgemmArgs g;
+  g.A = Kx + (size_t)r0 * ld + c0; g.sai = ld; g.sat = 1;        // X[r0 + i][c0 + t]
+  g.B = Kx + (size_t)cc0 * ld + c0; g.sbt = 1; g.sbj = ld;       // B(t, j) = X[cc0 + j][c0 + t]
+  g.C = Kx + (size_t)r0 * ld + cc0; g.ldc = ld;
+  g.M = M; g.N = N; g.K = Kd; g.lower_only = lower_only;
+  return dgemm_sub(g, st);
+}
+
+static int chol_lookahead(double* Kx, int n, int ld, int* info, cudaStream_t st) {
+  if (!g_chol_side) {
+    NIB_CUDA(cudaStreamCreateWithFlags(&g_chol_side, cudaStreamNonBlocking));
+    NIB_CUDA(cudaEventCreateWithFlags(&g_chol_ev_diag, cudaEventDisableTiming));
+    NIB_CUDA(cudaEventCreateWithFlags(&g_chol_ev_potrf, cudaEventDisableTiming));
+  }
+  cudaStream_t s2 = g_chol_side;
+  int rc;
+  auto potrf_side = [&](int k0, int nb) -> int {
+    // everything the main stream has queued so far (the update of this diagonal block) precedes the factorisation
+    NIB_CUDA(cudaEventRecord(g_chol_ev_diag, st));
+    NIB_CUDA(cudaStreamWaitEvent(s2, g_chol_ev_diag, 0));
+    potrf_diag_kernel<<<1, 256, TRTRI_SMEM, s2>>>(Kx, ld, k0, nb, info, g_dinv + (size_t)(k0 / NB) * NB * NB);
+    NIB_LAUNCH_CHECK();
+    NIB_CUDA(cudaEventRecord(g_chol_ev_potrf, s2));
+    return NIB_OK;
+  };
+  if ((rc = potrf_side(0, min(NB, n))) != NIB_OK) return rc;
+  for (int K0 = 0; K0 < n; K0 += NBC) {
+    const int W = min(NBC, n - K0);
+    for (int k0 = K0; k0 < K0 + W; k0 += NB) {
+      const int nb = min(NB, K0 + W - k0);
+      NIB_CUDA(cudaStreamWaitEvent(st, g_chol_ev_potrf, 0));      // block (k0, k0) is factored and inverted
+      const int t0 = k0 + nb, below = n - t0;
+      if (below <= 0) continue;
+      if ((rc = apply_dinv(g_dinv + (size_t)(k0 / NB) * NB * NB, Kx, ld, k0, nb, t0, below, 2, info, st)) != NIB_OK) return rc;
+      const bool in_block = t0 < K0 + W;
+      const int c0 = in_block ? k0 : K0, Kd = in_block ? nb : W;   // the panel whose outer product is subtracted
+      const int cend = in_block ? K0 + W : n;                      // ... from the columns [t0, cend)
+      const int nbn = min(NB, (in_block ? K0 + W : n) - t0);       // the next diagonal block
+      if ((rc = syrk_part(Kx, ld, t0, nbn, t0, nbn, c0, Kd, 1, st)) != NIB_OK) return rc;
+      if ((rc = potrf_side(t0, nbn)) != NIB_OK) return rc;
+      if ((rc = syrk_part(Kx, ld, t0 + nbn, n - (t0 + nbn), t0, nbn, c0, Kd, 0, st)) != NIB_OK) return rc;
+      if ((rc = syrk_part(Kx, ld, t0 + nbn, n - (t0 + nbn), t0 + nbn, cend - (t0 + nbn), c0, Kd, 1, st)) != NIB_OK) return rc;
+    }
+  }
+  NIB_CUDA(cudaStreamWaitEvent(st, g_chol_ev_potrf, 0));
+  return NIB_OK;
+}
+
 // ---- posterior pieces ------------------------------------------------------------------------
 __global__ void transpose_kernel(const double* __restrict__ in, int rows, int cols, int ldi, double* __restrict__ out,
                                  int ldo) {
@@ -1185,6 +1243,13 @@ int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream) {
     if ((rc = trtri_attrs()) != NIB_OK) return rc;
     static const bool rec = getenv("NIB_GP_CHOL_REC") != nullptr;   // fully recursive variant: measured slower (its
     if (rec) return chol_rec(d_K, ldk, 0, n, g_dinv, d_info, st);   // small symmetric updates leave most SMs idle)
+    // measured at n = 8192: 19.8 ms fit with the lookahead, 19.1 without — the update GEMMs hold every SM's registers
+    // (two 256-thread blocks of 128 registers), so the one-block factorisation on the side stream only gets an SM when
+    // a GEMM wave drains, and three GEMM launches per step instead of one cost more than that wins.  Opt-in.
+    static const bool la = getenv("NIB_GP_LOOKAHEAD") != nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (la && cap == cudaStreamCaptureStatusNone) return chol_lookahead(d_K, n, ldk, d_info, st);
     // Right-looking, two-level: 64-wide steps inside NBC-wide super-blocks.  Each step factors the diagonal block AND
     // inverts it (potrf_diag_kernel), turns the panel solve for every row below into one 64-deep product with that
     // inverse (apply_dinv_kernel) and updates the rest of the super-block's columns (rank 64); everything to the right of
