@@ -316,7 +316,8 @@ def test_score_vs_oracle(nib, N, K):
     np.testing.assert_allclose(s["max_prob"].cpu().numpy(), mp, rtol=2e-5, atol=1e-9)
 
 
-@pytest.mark.parametrize("K1,N1,N2,H", [(64, 256, 64, 12), (128, 512, 128, 9), (256, 1024, 256, 14), (256, 1024, 256, 5)])
+@pytest.mark.parametrize("K1,N1,N2,H", [(64, 256, 64, 12), (128, 512, 128, 9), (256, 1024, 256, 14), (256, 1024, 256, 5),
+                                        (128, 256, 128, 3), (192, 768, 256, 64)])   # M = 63: the pair's second tile is all padding; 224 tiles: several per pair
 def test_fused_expand_reduce_vs_torch(nib, K1, N1, N2, H):
     """conv_fused_ca_kernel: 1x1 expansion (+ residual, ReLU) and the next 1x1 reduction in one launch; both outputs (the
     N1-channel tensor that stays in global memory for the next residual, and the reduction) against torch fp32."""
