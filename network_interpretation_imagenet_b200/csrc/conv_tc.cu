@@ -1333,11 +1333,15 @@ struct TcFusedSmem {
   static constexpr int BAR_OFFSET = BIAS2_OFFSET + N2 * 4;
   static constexpr int NUM_BARS = 2 * S1 + 2 * S2 + 14;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
-  static constexpr int EP2_WARPS = N2 >= 128 ? 8 : 4;                // epilogue warps per CTA that drain acc2
+  static constexpr int EP2_WARPS = N2 / 16;                          // epilogue warps per CTA that drain acc2 (4 per 64 columns)
 };
 
+// 2 control warps + 16 epilogue warps: the kernel is bound by its epilogue (80 warp-boxes of ~2.6 kcycles per 128-row tile),
+// whose cost is latency, not issue slots, so the fix is more warps in flight; 32-column TMEM loads keep them under the
+// 113 registers a 576-thread block may use.
+static constexpr int TCF_THREADS = 64 + 512;
 template <int N2>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCF_THREADS, 1)
 conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                      const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmY,
                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut2,
@@ -1387,10 +1391,10 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
     for (int s = 0; s < S2; ++s) { mbar_init(full2(s), 1); mbar_init(empty2(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc1_full(b), 1);
-      mbar_init(acc1_empty(b), 8);     // 4 warps of warpgroup b in each CTA
+      mbar_init(acc1_empty(b), 16);    // 8 warps (both boxes of the chunk) in each CTA
       mbar_init(res_full(b), 1);
-      mbar_init(y_ready(b), 8);
-      mbar_init(stage_free(b), 5);     // MMA2 commit + the 4 warps whose stores read the set
+      mbar_init(y_ready(b), 16);
+      mbar_init(stage_free(b), 9);     // MMA2 commit + the 8 warps whose stores read the set
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 2 * SM::EP2_WARPS);
@@ -1536,9 +1540,11 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
       }
     }
   } else {
-    // ===== epilogue: warpgroup g = chunks of parity g, TMEM buffer g, staging set g =====
+    // ===== epilogue: 4 warpgroups.  Warpgroup G owns box h = G >> 1 (64 of the chunk's 128 columns) of the chunks of
+    // parity g = G & 1 (TMEM buffer g, staging set g), and 64 of the N2 output columns. =====
     const int ew = warp - 2;
-    const int g = ew >> 2;
+    const int G = ew >> 2;
+    const int g = G & 1, h = G >> 1;
     const int quarter = warp & 3;
     const uint32_t sw = (uint32_t)(lane & 7);
     const uint32_t lead_acc1_empty = mapa_shared(acc1_empty(g), 0);
@@ -1546,18 +1552,14 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
     const uint32_t lead_acc2_empty = mapa_shared(acc2_empty, 0);
     const uint32_t relu1_floor = p.relu1 ? 0u : 0xFF80FF80u;
     const uint32_t relu2_floor = p.relu2 ? 0u : 0xFF80FF80u;
-    constexpr bool EP2_ALL = N2 >= 128;
-    const bool ep2 = EP2_ALL || g == 0;
-    constexpr int UN2 = N2 >= 128 ? N2 / 128 : 1;        // 64-column boxes of acc2 per participating warpgroup
-    const int col2_base = EP2_ALL ? g * (N2 / 2) : 0;
+    const bool ep2 = G * 64 < N2;                        // this warpgroup drains columns [G*64, G*64+64) of acc2
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    // The warpgroup fetches its own residual chunks: one lane waits until the staging set is free again (its four warps'
-    // stores have read it and MMA2 has consumed it) and issues the TMA load for the warpgroup's next chunk right there
-    // (with the loads on the producer warp, its operand rings stalled behind every such wait).  The residual is added in
-    // place in the staging set, as in conv_tc3; fetching it global -> registers instead was measured slower (the loads'
-    // latency lands inside the epilogue math: 131 vs 114 kcycles per launch at the layer-3 shape).
+    const uint32_t slab = stg(g, h) + (uint32_t)(quarter * 4096);
+    const uint32_t obase = slab + (uint32_t)lane * 128u;
+    // one lane per parity fetches the set's residual chunk the moment the set is free again (its eight warps' stores have
+    // read it and MMA2 has consumed it); the residual is added in place in the staging set
     auto fetch_residual = [&](uint32_t use_next, int j_next, int m0_next) {
-      if (quarter == 0 && lane == 0) {
+      if (h == 0 && quarter == 0 && lane == 0) {
         FT(0, mbar_wait(stage_free(g), (use_next & 1u) ^ 1u, p.err_flag, 21));
         mbar_arrive_expect_tx(res_full(g), (uint32_t)(2 * SM::BOX_BYTES));
         tma_load_2d(stg(g, 0), &tmRes, res_full(g), j_next * 128, m0_next);
@@ -1569,8 +1571,32 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
       }
       __syncwarp();
     };
-    const int wt = (int)threadIdx.x - 64 - g * 128;                // 0..127 inside the warpgroup
+    const int wt = h * 128 + ((int)threadIdx.x - 64 - G * 128);    // 0..255 inside the parity group
     float* bias1_wg = bias1_s + g * 128;
+    // 32 accumulator columns -> bias (+ residual, in place) -> ReLU -> bf16 -> the slab's 16-byte chunks cbase..cbase+3
+    auto drain32 = [&](uint32_t taddr, const float* bsrc, int cbase, bool with_res, uint32_t floor_) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint64_t a0 = pack_f32x2(v[c * 8 + 0], v[c * 8 + 1]), a1 = pack_f32x2(v[c * 8 + 2], v[c * 8 + 3]);
+        uint64_t a2 = pack_f32x2(v[c * 8 + 4], v[c * 8 + 5]), a3 = pack_f32x2(v[c * 8 + 6], v[c * 8 + 7]);
+        const float4 b0 = *reinterpret_cast<const float4*>(bsrc + c * 8), b1 = *reinterpret_cast<const float4*>(bsrc + c * 8 + 4);
+        a0 = add_f32x2(a0, pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)));
+        a1 = add_f32x2(a1, pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)));
+        a2 = add_f32x2(a2, pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)));
+        a3 = add_f32x2(a3, pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w)));
+        const uint32_t addr = obase + ((((uint32_t)(cbase + c)) ^ sw) << 4);
+        if (with_res) {
+          const uint4 r = lds_v4(addr);                                  // 8 bf16 residual values of this row
+          a0 = add_f32x2(a0, pack_f32x2(r.x << 16, r.x & 0xFFFF0000u)); a1 = add_f32x2(a1, pack_f32x2(r.y << 16, r.y & 0xFFFF0000u));
+          a2 = add_f32x2(a2, pack_f32x2(r.z << 16, r.z & 0xFFFF0000u)); a3 = add_f32x2(a3, pack_f32x2(r.w << 16, r.w & 0xFFFF0000u));
+        }
+        sts_v4(addr, make_uint4(max_bf16x2(cvt_bf16x2(a0), floor_), max_bf16x2(cvt_bf16x2(a1), floor_),
+                                max_bf16x2(cvt_bf16x2(a2), floor_), max_bf16x2(cvt_bf16x2(a3), floor_)));
+      }
+    };
     if (pair < m_pairs) fetch_residual(0u, g, (pair * 2 + (int)rank) * TC_BLOCK_M);
     int it = 0;
     for (int tile = pair; tile < m_pairs; tile += npairs, ++it) {
@@ -1579,58 +1605,34 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
       const int m0_next = ((tile + npairs) * 2 + (int)rank) * TC_BLOCK_M;
       for (int j = g; j < p.nch; j += 2) {
         const uint32_t use = (uint32_t)((it * p.nch + j) >> 1);
-        // this chunk's 128 bias values: one per thread into the warpgroup's window (the previous chunk's readers are past
-        // the named barrier of their own chunk; the barrier below orders this write against them and publishes it)
-        const float bias_reg = p.bias1 ? __ldg(p.bias1 + j * 128 + wt) : 0.f;
-        named_bar_sync(1 + g, 128);
-        bias1_wg[wt] = bias_reg;
-        named_bar_sync(1 + g, 128);
+        // this chunk's 128 bias values into the parity group's window (256 threads; the barrier pair orders the write
+        // against the previous chunk's readers and publishes it)
+        const float bias_reg = (wt < 128 && p.bias1) ? __ldg(p.bias1 + j * 128 + wt) : 0.f;
+        named_bar_sync(1 + g, 256);
+        if (wt < 128) bias1_wg[wt] = bias_reg;
+        named_bar_sync(1 + g, 256);
         FT(1, mbar_wait(res_full(g), use & 1u, p.err_flag, 29));
         FT(2, mbar_wait(acc1_full(g), use & 1u, p.err_flag, 30));
         tc_fence_after();
-#pragma unroll 1
-        for (int b = 0; b < 2; ++b) {
-          const uint32_t slab = stg(g, b) + (uint32_t)(quarter * 4096);
-          const uint32_t obase = slab + (uint32_t)lane * 128u;
-          uint32_t v[64];
-          __syncwarp();
-          tmem_ld_32x32b_x64(lane_taddr + (uint32_t)(g * 128 + b * 64), v);
-          tmem_ld_wait();
-          if (b == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(lead_acc1_empty);
-          }
-          const float* bsrc = bias1_wg + b * 64;
-          uint32_t o[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint64_t a0 = pack_f32x2(v[c * 8 + 0], v[c * 8 + 1]), a1 = pack_f32x2(v[c * 8 + 2], v[c * 8 + 3]);
-            uint64_t a2 = pack_f32x2(v[c * 8 + 4], v[c * 8 + 5]), a3 = pack_f32x2(v[c * 8 + 6], v[c * 8 + 7]);
-            const float4 b0 = *reinterpret_cast<const float4*>(bsrc + c * 8), b1 = *reinterpret_cast<const float4*>(bsrc + c * 8 + 4);
-            a0 = add_f32x2(a0, pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)));
-            a1 = add_f32x2(a1, pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)));
-            a2 = add_f32x2(a2, pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)));
-            a3 = add_f32x2(a3, pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w)));
-            const uint4 r = lds_v4(obase + ((((uint32_t)c) ^ sw) << 4));   // 8 bf16 residual values of this row
-            a0 = add_f32x2(a0, pack_f32x2(r.x << 16, r.x & 0xFFFF0000u)); a1 = add_f32x2(a1, pack_f32x2(r.y << 16, r.y & 0xFFFF0000u));
-            a2 = add_f32x2(a2, pack_f32x2(r.z << 16, r.z & 0xFFFF0000u)); a3 = add_f32x2(a3, pack_f32x2(r.w << 16, r.w & 0xFFFF0000u));
-            o[c * 4 + 0] = max_bf16x2(cvt_bf16x2(a0), relu1_floor); o[c * 4 + 1] = max_bf16x2(cvt_bf16x2(a1), relu1_floor);
-            o[c * 4 + 2] = max_bf16x2(cvt_bf16x2(a2), relu1_floor); o[c * 4 + 3] = max_bf16x2(cvt_bf16x2(a3), relu1_floor);
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts_v4(obase + ((((uint32_t)c) ^ sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
-          fence_async_smem();   // generic-proxy writes -> visible to the TMA store and to tcgen05.mma (async proxy)
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmY, slab, j * 128 + b * 64, m0 + quarter * 32);
-            bulk_commit();
-          }
-        }
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_y_ready);      // release at cluster scope: the leader's MMA reads this CTA's set
-        const bool defer = ep2 && (j + 2 >= p.nch);            // the set is reused by EPI2 before it goes back to the producer
+        FT(6, drain32(lane_taddr + (uint32_t)(g * 128 + h * 64), bias1_wg + h * 64, 0, true, relu1_floor));
+        FT(6, drain32(lane_taddr + (uint32_t)(g * 128 + h * 64 + 32), bias1_wg + h * 64 + 32, 4, true, relu1_floor));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(lead_acc1_empty);
+        FT(4, fence_async_smem());   // generic-proxy writes -> visible to the TMA store and to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          // Signal first, store second, and a plain (CTA-scope release) remote arrive: `arrive.release.cluster` issued
+          // behind the bulk store cost ~3 kcycles per chunk and was the largest single item of the epilogue's time
+          // (118 -> 110 kcycles per launch by reordering, -> 94 with the plain arrive).  What orders the box against
+          // MMA2 is the fence.proxy.async above — the tensor core of THIS SM reads this CTA's box through the async
+          // proxy — followed in program order by the arrive; conv_tc3's cross-CTA handshakes use the same arrive.
+          FT(5, mbar_arrive_remote(lead_y_ready));
+          tma_store_2d(&tmY, slab, j * 128 + h * 64, m0 + quarter * 32);
+          bulk_commit();
+        }
+        const bool defer = ep2 && (j + 2 >= p.nch);            // the slab is reused by EPI2 before the set goes back
         if (!defer) {
           if (lane == 0) {
             bulk_wait_read<0>();
@@ -1644,53 +1646,27 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
       if (ep2) {
         FT(3, mbar_wait(acc2_full, (uint32_t)it & 1u, p.err_flag, 31));
         tc_fence_after();
-        if (lane == 0) bulk_wait_read<0>();     // the y stores of this warp's last chunk have read the set
+        if (lane == 0) bulk_wait_read<0>();     // the y store of this warp's last chunk has read the slab
         __syncwarp();
-#pragma unroll 1
-        for (int u = 0; u < UN2; ++u) {
-          const int col2 = col2_base + u * 64;
-          const uint32_t slab = stg(g, u) + (uint32_t)(quarter * 4096);
-          const uint32_t obase = slab + (uint32_t)lane * 128u;
-          uint32_t v[64];
-          __syncwarp();
-          tmem_ld_32x32b_x64(lane_taddr + ACC2_COL + (uint32_t)col2, v);
-          tmem_ld_wait();
-          if (u == UN2 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(lead_acc2_empty);
-          }
-          const float* bsrc = bias2_s + col2;
-          uint32_t o[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint64_t a0 = pack_f32x2(v[c * 8 + 0], v[c * 8 + 1]), a1 = pack_f32x2(v[c * 8 + 2], v[c * 8 + 3]);
-            uint64_t a2 = pack_f32x2(v[c * 8 + 4], v[c * 8 + 5]), a3 = pack_f32x2(v[c * 8 + 6], v[c * 8 + 7]);
-            const float4 b0 = *reinterpret_cast<const float4*>(bsrc + c * 8), b1 = *reinterpret_cast<const float4*>(bsrc + c * 8 + 4);
-            a0 = add_f32x2(a0, pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)));
-            a1 = add_f32x2(a1, pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)));
-            a2 = add_f32x2(a2, pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)));
-            a3 = add_f32x2(a3, pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w)));
-            o[c * 4 + 0] = max_bf16x2(cvt_bf16x2(a0), relu2_floor); o[c * 4 + 1] = max_bf16x2(cvt_bf16x2(a1), relu2_floor);
-            o[c * 4 + 2] = max_bf16x2(cvt_bf16x2(a2), relu2_floor); o[c * 4 + 3] = max_bf16x2(cvt_bf16x2(a3), relu2_floor);
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts_v4(obase + ((((uint32_t)c) ^ sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut2, slab, col2, m0 + quarter * 32);
-            bulk_commit();
-          }
-        }
+        const int col2 = G * 64;
+        drain32(lane_taddr + ACC2_COL + (uint32_t)col2, bias2_s + col2, 0, false, relu2_floor);
+        drain32(lane_taddr + ACC2_COL + (uint32_t)(col2 + 32), bias2_s + col2 + 32, 4, false, relu2_floor);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(lead_acc2_empty);
+        fence_async_smem();
+        __syncwarp();
         if (lane == 0) {
+          tma_store_2d(&tmOut2, slab, col2, m0 + quarter * 32);
+          bulk_commit();
           bulk_wait_read<0>();
           mbar_arrive(stage_free(g));
         }
         __syncwarp();
-        if (more_tiles) fetch_residual((uint32_t)(((it + 1) * p.nch + g) >> 1), g, m0_next);
       }
+      // a warpgroup that took part in EPI2 handed its slab back only now: its parity's residual lane queues the next
+      // tile's first chunk here (the others did so from inside the chunk loop)
+      if (ep2 && more_tiles) fetch_residual((uint32_t)((it * p.nch + (p.nch - 2 + g)) >> 1) + 1u, g, m0_next);
     }
     if (lane == 0) bulk_wait_read<0>();
     tc_fence_before();
@@ -2067,7 +2043,7 @@ static int launch_fused(const TcFusedPlan* plan, const TcFusedParams& kp, cudaSt
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(TC3_THREADS);
+  cfg.blockDim = dim3(TCF_THREADS);
   cfg.dynamicSmemBytes = SM::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -2116,7 +2092,7 @@ int tc_fused_launch(const TcFusedPlan* plan, const ConvParams& c, const ConvPara
     }
     fprintf(stderr, "[fused K1=%d N1=%d N2=%d M=%d] leader-CTA averages (kcycles)\n", c.Cin, c.Cout, a.Cout, c.M);
     const char* names[4] = {"producer: a1_empty empty1 empty2 - - - - | total", "mma: acc1_empty a1_full full1 y_ready acc2_empty full2 - | total",
-                            "epi wg0: stage_free res_full acc1_full acc2_full - - - | total", "epi wg1: stage_free res_full acc1_full acc2_full - - - | total"};
+                            "epi wg0: stage_free res_full acc1_full acc2_full fence_async arrive_cluster drain | total", "epi wg1: stage_free res_full acc1_full acc2_full fence_async arrive_cluster drain | total"};
     for (int r = 0; r < 4; ++r) {
       fprintf(stderr, "  %s\n   ", names[r]);
       for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.1f", avg[r * 8 + i] / n / 1e3);
