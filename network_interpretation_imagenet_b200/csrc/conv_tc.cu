@@ -1598,6 +1598,7 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
       }
     };
     if (pair < m_pairs) fetch_residual(0u, g, (pair * 2 + (int)rank) * TC_BLOCK_M);
+    float bias_next = (wt < 128 && p.bias1) ? __ldg(p.bias1 + g * 128 + wt) : 0.f;
     int it = 0;
     for (int tile = pair; tile < m_pairs; tile += npairs, ++it) {
       const int m0 = (tile * 2 + (int)rank) * TC_BLOCK_M;
@@ -1607,10 +1608,14 @@ conv_fused_ca_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_cons
         const uint32_t use = (uint32_t)((it * p.nch + j) >> 1);
         // this chunk's 128 bias values into the parity group's window (256 threads; the barrier pair orders the write
         // against the previous chunk's readers and publishes it)
-        const float bias_reg = (wt < 128 && p.bias1) ? __ldg(p.bias1 + j * 128 + wt) : 0.f;
+        const float bias_reg = bias_next;
         named_bar_sync(1 + g, 256);
         if (wt < 128) bias1_wg[wt] = bias_reg;
         named_bar_sync(1 + g, 256);
+        {   // the NEXT chunk's bias is fetched now: a load issued at the top of its own chunk sat on the critical path
+          const int jn = (j + 2 < p.nch) ? j + 2 : g;
+          bias_next = (wt < 128 && p.bias1) ? __ldg(p.bias1 + jn * 128 + wt) : 0.f;
+        }
         FT(1, mbar_wait(res_full(g), use & 1u, p.err_flag, 29));
         FT(2, mbar_wait(acc1_full(g), use & 1u, p.err_flag, 30));
         tc_fence_after();
