@@ -64,12 +64,12 @@ def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the tcgen05 conv launches of ONE micro-batch-256 forward, from the
     committed ncu capture (profiles/, one pass with cache control on: cold-L2 per launch), averaged per launch."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01_ncu_all_launches_one_forward_v3_mb256.csv")
+    p = os.path.join(ROOT, "profiles", "r01_ncu_all_launches_one_forward_v6_mb256.csv")
     if not os.path.exists(p):
         return None, None
     tot, n = 0.0, 0
     for r in csv.DictReader(open(p)):
-        if r["kernel"].startswith("conv_tc"):
+        if r["kernel"].startswith("conv_tc") or r["kernel"].startswith("conv_fused"):
             tot += float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])
             n += 1
     return (tot / n if n else None), n
@@ -333,7 +333,7 @@ def run_ours(args):
             roofline = {"bound": "tensor", "kernel": "conv_tc3_kernel + conv_fused_ca_kernel (tcgen05 cta_group::2 implicit GEMM)", "achieved": ach,
                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
-                        "traffic_source": "profiles/r01_ncu_all_launches_one_forward_v3_mb256.csv: mean DRAM bytes per conv "
+                        "traffic_source": "profiles/r01_ncu_all_launches_one_forward_v6_mb256.csv: mean DRAM bytes per conv "
                                           "launch (ncu, cold L2 per launch), scaled to this micro-batch",
                         "algorithmic_bytes_per_launch": ACT_BYTES_PER_EVAL * min(mb, per) / n_tc,
                         "flops_per_launch": tc_fl / n_tc,
