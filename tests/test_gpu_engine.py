@@ -125,3 +125,20 @@ def test_two_rank_sharding_matches_single_gpu(nib):
                         "--master-addr", "127.0.0.1", "--master-port", "29611",
                         os.path.join(ROOT, "tests", "multi_gpu_worker.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_resnet101_forward_is_bitwise_reproducible(nib):
+    """Race hunt for the fused expansion+reduction launches (smem boxes handed from epilogue warps of both CTAs of a pair
+    to the tensor core): repeated forwards over two stream copies must reproduce the logits bit for bit."""
+    from network_interpretation_imagenet_b200.classifier import Classifier
+    from network_interpretation_imagenet_b200.masks import MaskSynth
+    x = synthetic.synthetic_image("imagenet")
+    seg = synthetic.voronoi_labels(224, 224, 50)
+    model = ocls.build_imagenet_model("resnet101")
+    synth = MaskSynth(x, seg, S=50, device="cuda")
+    sels = nib.draw_selections("subset_keep", 50, 111, seed=5)
+    bits = torch.from_numpy(nib.selection_bits(sels, 50).view(np.int64)).cuda()
+    clf = Classifier.from_torch(model, (224, 224), precision="bf16", max_batch=37, streams=2)
+    ref = clf.forward_masked(synth, bits, nib.KEEP_MUL).clone()
+    for _ in range(8):
+        assert torch.equal(clf.forward_masked(synth, bits, nib.KEEP_MUL), ref)
