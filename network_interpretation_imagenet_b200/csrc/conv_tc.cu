@@ -10,7 +10,12 @@
 // Both land as a 128 x 64 bf16, 128B-swizzled, K-major tile = one tcgen05.mma operand.
 // Weights are KRSC ([Cout][R*S*Cin], BN folded) and arrive through a second tiled map.
 //
-// CTA = 192 threads, warp-specialised:  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
+// Four kernels live in this file, oldest first: conv_tc_kernel (v1, described next; still serves Cout = 32 tiles and the
+// fp32-output GEMM self-test), conv_tc2_kernel (v2: persistent, TMA-store epilogue), conv_tc3_kernel (v3, the default: CTA
+// pairs with tcgen05 cta_group::2) and conv_fused_ca_kernel (a 1x1 expansion + the next 1x1 reduction in one launch).
+// DESIGN.md section 4 has the measurements that led from one to the next.
+//
+// v1: CTA = 192 threads, warp-specialised:  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
 // (warp 1 also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> bias /
 // residual / ReLU -> bf16 -> global).  The accumulator (128 lanes x BLOCK_N fp32 columns) lives
 // in TMEM; smem holds a STAGES-deep ring of (A, B) tiles guarded by full/empty mbarriers.
