@@ -94,7 +94,9 @@ def bayesian_optimisation_masks(n_iters, score_masks, train_bits, train_scores, 
                                 length_scale=None, n_restarts_optimizer=0, refit_every=0, random_state=0):
     """Active learning over masks (BASELINE config 4: `n_iters` rounds on n training masks, m candidates).
 
-    score_masks(bits[k, words]) -> np.ndarray[k] target-class probabilities (PerturbationEngine.score_masks).
+    score_masks(bits[k, words]) -> np.ndarray[k] target-class probabilities, e.g.
+    `lambda b: engine.score_masks(b)["target_prob"].cpu().numpy()` (PerturbationEngine.score_masks itself returns a dict
+    of device tensors).
     Each round: GP fit on (train_bits, train_scores) -> posterior mean/std on every remaining candidate -> EI
     (greater_is_better, as reference :175) -> arg-max candidate is evaluated and appended."""
     import torch

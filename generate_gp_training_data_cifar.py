@@ -63,7 +63,9 @@ def eval_superpixel(args):
     output = model.module(torch.from_numpy(image)[None].cuda())     # :301-302
     pred = int(output.argmax(1)[0])
     target = pred if args.target is None else args.target
-    res = run_generator("cifar", model.module.engine((32, 32)), image, target, args.num_mask_samples, args.mask_seed,
+    # bf16: hand over the torch module so the engine can also lower the fp32 copy its tie policy re-scores with
+    net = model.module if args.precision == "bf16" else model.module.engine((32, 32))
+    res = run_generator("cifar", net, image, target, args.num_mask_samples, args.mask_seed,
                         precision=args.precision, max_batch=args.batch_size,
                         mask_dir=None if args.no_write else "./masks")
     return res["correct_pred_count"], res["wrong_pred_count"]

@@ -63,14 +63,15 @@ def load_image(args) -> np.ndarray:
 def validate(model, image, args):
     """The reference's validate(): returns correct_pred_count (:268) or 0 when the unmasked image is misclassified."""
     from network_interpretation_imagenet_b200.classifier import Classifier
-    net = Classifier.from_torch(model, (224, 224), precision=args.precision, max_batch=args.batch_size)
-    logits = net.forward(torch.from_numpy(image)[None].cuda())
+    # the unmasked image decides `target` (:190-200): one image, scored by the fp32 lowering
+    logits = Classifier.from_torch(model, (224, 224), precision="fp32", max_batch=1).forward(torch.from_numpy(image)[None].cuda())
     pred = int(logits.argmax(1)[0])
     target = pred if args.target is None else args.target
     if pred != target:
         print("wrong prediction")
         return 0
-    res = run_generator("imagenet_subset" if args.subset else "imagenet", net, image, target, args.num_mask_samples,
+    # the torch module (not a lowered Classifier) goes in, so the engine can lower the fp32 copy its tie policy needs
+    res = run_generator("imagenet_subset" if args.subset else "imagenet", model, image, target, args.num_mask_samples,
                         args.mask_seed, precision=args.precision, max_batch=args.batch_size,
                         mask_dir=None if args.no_write else "./masks")
     return res["correct_pred_count"]

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NIB_ABI_VERSION 1
+#define NIB_ABI_VERSION 2   /* 2: + tie policy, device-side batch size, NCCL score all-gather, threshold/bbox helpers */
 
 enum nib_status {
   NIB_OK = 0,
@@ -190,7 +190,8 @@ int nib_net_set_graph(nib_net* net, int enable);
 
 /* Per-op device timing of one forward (CUDA events on `stream` around every launch; the input buffer must
  * already hold N images, e.g. from a previous nib_net_forward_masked).  Arrays are host, length >= cap;
- * *num_ops receives the op count.  h_kind: 0 SIMT conv, 1 tcgen05 conv, 2 pool, 3 fc.
+ * *num_ops receives the op count.  h_kind: 0 SIMT conv, 1 tcgen05 conv, 2 pool, 3 fc, 4 tcgen05 conv that ran inside the
+ * previous op's fused launch (no launch of its own).
  * h_flops: 2*M*K*Cout for convs / fc (the algorithmic FLOPs SURVEY.md §8d counts), 0 for pools.
  * h_geom (optional, 8 ints per op): Hout, Wout, Cin, Cout, R, stride, has_residual, block_n. */
 int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flops, int* h_geom,
@@ -205,6 +206,47 @@ int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flo
 int nib_score(const float* d_logits, int N, int K, int target, int32_t* d_top1,
               float* d_target_prob, float* d_max_prob, uint8_t* d_correct, float* d_margin,
               void* stream);
+
+/* nib_score plus d_table [N][2] fp32 = (target_prob, (float)top1) per row: the layout of the score all-gather's send
+ * buffer (class ids < 2^24 are exact in fp32), written by the same kernel so no packing pass sits between scoring and
+ * the collective.  Any output pointer may be NULL. */
+int nib_score_table(const float* d_logits, int N, int K, int target, int32_t* d_top1,
+                    float* d_target_prob, float* d_max_prob, uint8_t* d_correct, float* d_margin,
+                    float* d_table, void* stream);
+
+/* Tie policy of the bf16 path, entirely on the stream (no host synchronisation).  The reference compares the arg-max
+ * of fp32 logits with the target (imagenet :248-257); bf16 logits are within a stated tolerance of those, so rows whose
+ * top-2 margin is inside the band are re-scored by an fp32 copy of the classifier:
+ *   nib_tie_compact  d_idx[cap] <- ascending row indices with d_margin[r] < threshold (first `cap` of them; unused
+ *                    slots -1), d_sel_out[cap][words] <- their selection words (unused slots 0), *d_count <- how many
+ *                    rows qualified in total (> cap means overflow: the rows beyond the buffer keep their bf16 score);
+ *                    d_totals (optional, int64[2]) accumulates (qualified, did-not-fit) over calls
+ *   nib_net_set_dynamic_batch + nib_net_forward_masked(N = cap) on the fp32 network: only *d_count images are computed
+ *   nib_tie_scatter  refined results of slot s < min(*d_count, cap) overwrite row d_idx[s] of the score arrays / table */
+int nib_tie_compact(const float* d_margin, int N, float threshold, const uint64_t* d_sel, int words, int cap,
+                    int32_t* d_idx, uint64_t* d_sel_out, int32_t* d_count, long long* d_totals, void* stream);
+int nib_tie_scatter(const int32_t* d_idx, const int32_t* d_count, int cap, const int32_t* r_top1,
+                    const float* r_target_prob, const float* r_max_prob, const uint8_t* r_correct,
+                    int32_t* d_top1, float* d_target_prob, float* d_max_prob, uint8_t* d_correct,
+                    float* d_table, void* stream);
+/* fp32 (CUDA-core) networks only: the kernels of every following forward read the live image count from *d_count
+ * (clamped to the N passed to the call) and skip the rest of the batch; NULL restores host-side N. */
+int nib_net_set_dynamic_batch(nib_net* net, const int32_t* d_count);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: the path's only exchange step.  Rank r of W scores masks [r*per, (r+1)*per) (contiguous shards of the
+ * global, seed-generated selection table) and every rank receives the whole (target_prob, top1) table — the GP rank fits
+ * on all of it.  The reference declares --world-size / --dist-backend (generate_gp_training_data_imagenet.py:72-77) and
+ * stops at `args.distributed = args.world_size > 1` (:572).  NCCL is bound at run time (dlopen; PyTorch's copy is reused
+ * when loaded).  Bootstrap: rank 0 calls nib_comm_unique_id, the 128 bytes travel by any side channel
+ * (torch.distributed broadcast in the host mirror), every rank calls nib_comm_init.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nib_comm nib_comm;
+int nib_comm_unique_id(void* h_id128);
+int nib_comm_init(const void* h_id128, int rank, int world, nib_comm** out);
+int nib_comm_destroy(nib_comm* comm);
+/* d_local [rows_per_rank][2] fp32 (nib_score_table's d_table) -> d_table [world*rows_per_rank][2], rank-major */
+int nib_allgather_scores(nib_comm* comm, const float* d_local, int rows_per_rank, float* d_table, void* stream);
 
 /* Standalone tcgen05 GEMM self-test hook: C[M,N] = A[M,K] * B[N,K]^T (bf16 in, fp32 out).
  * Used by tests to validate descriptors independent of the network executor. */

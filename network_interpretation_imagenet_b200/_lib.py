@@ -13,6 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libnib.so")
 
 NIB_OK = 0
+ABI_VERSION = 2
 MASK_KEEP_MUL, MASK_REMOVE_MINMAX = 0, 1
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
@@ -76,6 +77,14 @@ _PROTOTYPES = {
     "nib_net_set_graph": (_i, [_vp, _i]),
     "nib_net_profile": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(_i), _vp]),
     "nib_score": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nib_score_table": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nib_tie_compact": (_i, [_vp, _i, C.c_float, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "nib_tie_scatter": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nib_net_set_dynamic_batch": (_i, [_vp, _vp]),
+    "nib_comm_unique_id": (_i, [_vp]),
+    "nib_comm_init": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "nib_comm_destroy": (_i, [_vp]),
+    "nib_allgather_scores": (_i, [_vp, _vp, _i, _vp, _vp]),
     "nib_tc_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "nib_gp_gram_binary": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _vp, _i, _vp]),
     "nib_gp_gram_rbf": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _i, _vp, _i, _vp]),
@@ -116,8 +125,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.nib_abi_version() != 1:
-        raise ImportError(f"libnib.so ABI version {lib.nib_abi_version()} != 1; rebuild")
+    if lib.nib_abi_version() != ABI_VERSION:
+        raise ImportError(f"libnib.so ABI version {lib.nib_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = lib
     return lib
 

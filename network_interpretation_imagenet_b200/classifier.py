@@ -230,6 +230,8 @@ class Classifier:
         N = int(d_sel.shape[0])
         if out is None:
             out = torch.empty(N, self.num_classes, dtype=torch.float32, device=d_sel.device)
+        if mode == _lib.MASK_REMOVE_MINMAX:
+            synth.seg_minmax()   # computed (once) on the caller's stream, before the side streams fork from it
 
         def launch(c, i, n):
             a = synth.mask_args(d_sel[i:i + n], mode, None, 0, 0)

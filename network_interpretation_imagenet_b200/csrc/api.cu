@@ -1,6 +1,9 @@
 // api.cu — error plumbing and device probing for the C ABI (include/nib.h).
 #include "common.cuh"
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace nib {
 
@@ -47,6 +50,30 @@ int check_device() {
 int num_sms() {
   if (g_num_sms == 0) check_device();
   return g_num_sms > 0 ? g_num_sms : 148;
+}
+
+// Library scratch is keyed by (use, device, stream): work submitted to one stream is ordered, so the next call on that
+// stream may reuse the buffer, while calls on other streams (classifier.py feeds stream copies concurrently) get their
+// own.  Growing a buffer goes through cudaFree, which waits for the kernels still reading the old one.
+struct ScratchBuf { void* ptr; size_t cap; };
+static std::map<std::pair<std::pair<int, int>, cudaStream_t>, ScratchBuf> g_scratch_bufs;
+static std::mutex g_scratch_mu;
+
+int stream_scratch(int slot, cudaStream_t st, size_t bytes, size_t min_bytes, void** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  ScratchBuf& b = g_scratch_bufs[{{slot, dev}, st}];
+  if (b.cap < bytes) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+    const size_t want = bytes < min_bytes ? min_bytes : bytes;
+    NIB_CUDA(cudaMalloc(&b.ptr, want));
+    b.cap = want;
+  }
+  *out = b.ptr;
+  return NIB_OK;
 }
 
 }  // namespace nib

@@ -30,6 +30,11 @@ conv_simt_kernel(ConvParams p) {
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int K = p.R * p.S * p.Cin;
+  if (p.dyn_n != nullptr) {   // device-side live batch: whole blocks beyond it leave before the first barrier
+    const long long live = (long long)max(*p.dyn_n, 0) * p.P * p.Q;
+    if (live < p.M) p.M = (int)live;
+    if (m0 >= p.M) return;
+  }
 
   // A-load role: one pixel per thread (tid % 128), 8 consecutive k (tid / 128)
   const int a_pix = tid & (BM - 1);
@@ -194,7 +199,8 @@ __global__ void pool_kernel(PoolParams p) {
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)p.N * p.P * p.Q * p.C;
+  const int Nl = p.dyn_n ? min(max(*p.dyn_n, 0), p.N) : p.N;
+  long long total = (long long)Nl * p.P * p.Q * p.C;
   if (idx >= total) return;
   int c = (int)(idx % p.C);
   long long t = idx / p.C;
@@ -224,7 +230,8 @@ pool_bf16x8_kernel(PoolParams p) {
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
   const int C8 = p.C >> 3;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)p.N * p.P * p.Q * C8;
+  const int Nl = p.dyn_n ? min(max(*p.dyn_n, 0), p.N) : p.N;
+  long long total = (long long)Nl * p.P * p.Q * C8;
   if (idx >= total) return;
   const int c = (int)(idx % C8) * 8;
   long long t = idx / C8;
@@ -331,11 +338,15 @@ static constexpr int FC_BM = 32, FC_BN = 64, FC_BK = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 fc_kernel(const T* __restrict__ feat, int feat_stride, const float* __restrict__ w, const float* __restrict__ b,
-          int N, int Cin, int Cout, float* __restrict__ logits) {
+          int N, int Cin, int Cout, float* __restrict__ logits, const int* __restrict__ dyn_n) {
   __shared__ float Fs[FC_BK][FC_BM + 2];
   __shared__ __align__(16) float Ws[FC_BK][FC_BN + 4];
   const int tid = threadIdx.x;
   const int n0 = blockIdx.y * FC_BM, k0 = blockIdx.x * FC_BN;
+  if (dyn_n != nullptr) {
+    N = min(max(*dyn_n, 0), N);
+    if (n0 >= N) return;
+  }
   const int ty = tid >> 4, tx = tid & 15;   // samples 2ty, 2ty+1; classes 4tx..4tx+3
   // loader roles: feature element (row fr, k fc*4..+3); weight elements (row wr and wr+32, k wc*4..+3)
   const int fr = tid >> 3, fc = tid & 7;
@@ -385,12 +396,12 @@ fc_kernel(const T* __restrict__ feat, int feat_stride, const float* __restrict__
 }
 
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
-              int Cout, float* logits, cudaStream_t st) {
+              int Cout, float* logits, const int* dyn_n, cudaStream_t st) {
   dim3 grid(ceil_div(Cout, FC_BN), ceil_div(N, FC_BM));
   if (bf16)
-    fc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)feat, feat_stride, w, b, N, Cin, Cout, logits);
+    fc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)feat, feat_stride, w, b, N, Cin, Cout, logits, dyn_n);
   else
-    fc_kernel<float><<<grid, 256, 0, st>>>((const float*)feat, feat_stride, w, b, N, Cin, Cout, logits);
+    fc_kernel<float><<<grid, 256, 0, st>>>((const float*)feat, feat_stride, w, b, N, Cin, Cout, logits, dyn_n);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }

@@ -2006,6 +2006,13 @@ bool tc_fuse_supported(const ConvParams& c, const ConvParams& a) {
   if (a.in != c.out || a.Cin != c.Cout || a.res != nullptr) return false;
   if (a.Cout != 64 && a.Cout != 128 && a.Cout != 256) return false;
   if (a.P != c.P || a.Q != c.Q || a.M != c.M) return false;
+  // Buffer aliasing.  classifier.py's LIFO buffer pool usually hands the reduction's output the very buffer the expansion
+  // reads its A operand from (a.out == c.in).  The kernel tolerates exactly that case: a CTA pair loads the whole A tile
+  // of its 256 rows before the tile's last MMA1, Out2 of those rows is data-dependent on all of it, and no other pair
+  // touches these rows - provided both tensors have the same row pitch, so "these rows" are the same bytes.  Every other
+  // overlap (y or Out2 over the residual, y over A) would be a write-after-read race between pairs: not fused.
+  if (a.out == c.in && (a.Cout != c.Cin || a.out_cstride != c.in_cstride || a.out_coff != c.in_coff)) return false;
+  if (a.out == c.res || c.out == c.res || c.out == c.in) return false;
   return true;
 }
 

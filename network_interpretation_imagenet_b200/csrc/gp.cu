@@ -452,17 +452,10 @@ static int trtri_attrs() {
   return NIB_OK;
 }
 
-// scratch for the diagonal-block inverses of the factor currently being built / solved with
-static double* g_dinv = nullptr;
-static size_t g_dinv_cap = 0;
-static int ensure_dinv(int n) {
-  const size_t need = (size_t)ceil_div(n, NB) * NB * NB;
-  if (g_dinv_cap < need) {
-    if (g_dinv) cudaFree(g_dinv);
-    g_dinv_cap = need < (size_t)256 * NB * NB ? (size_t)256 * NB * NB : need;
-    NIB_CUDA(cudaMalloc(&g_dinv, g_dinv_cap * sizeof(double)));
-  }
-  return NIB_OK;
+// scratch for the diagonal-block inverses of the factor currently being built / solved with (per stream, common.cuh)
+static int get_dinv(int n, cudaStream_t st, double** dinv) {
+  const size_t need = (size_t)ceil_div(n, NB) * NB * NB * sizeof(double);
+  return stream_scratch(SCRATCH_GP_DINV, st, need, (size_t)256 * NB * NB * sizeof(double), reinterpret_cast<void**>(dinv));
 }
 static inline int split64(int w) { return ((w / 2 + NB - 1) / NB) * NB; }   // NB <= split < w for w > NB
 
@@ -724,14 +717,10 @@ trsv_step_kernel(const double* __restrict__ Lm, int ldl, double* __restrict__ b,
   }
 }
 
-static double* g_trsv_x = nullptr;
-static size_t g_trsv_cap = 0;
 static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, const double* dinv, cudaStream_t st) {
-  if (g_trsv_cap < (size_t)n) {
-    if (g_trsv_x) cudaFree(g_trsv_x);
-    g_trsv_cap = (size_t)n < 16384 ? 16384 : (size_t)n;
-    NIB_CUDA(cudaMalloc(&g_trsv_x, g_trsv_cap * sizeof(double)));
-  }
+  double* g_trsv_x = nullptr;
+  int rcs = stream_scratch(SCRATCH_GP_TRSV, st, (size_t)n * sizeof(double), 16384 * sizeof(double), reinterpret_cast<void**>(&g_trsv_x));
+  if (rcs != NIB_OK) return rcs;
   const int nblk = ceil_div(n, NB);
   for (int s = 0; s < nblk; ++s) {
     const int blk = trans ? nblk - 1 - s : s;
@@ -866,13 +855,14 @@ static bool gp_v1() {
 static int trsm_impl(const double* L, int n, int ldl, double* B, int nrhs, int ldb, int trans, cudaStream_t st) {
   if (n <= 0 || nrhs <= 0) return NIB_OK;
   if (gp_v1()) return trsm_impl_v1(L, n, ldl, B, nrhs, ldb, trans, st);
-  int rc = ensure_dinv(n);
+  double* dinv = nullptr;
+  int rc = get_dinv(n, st, &dinv);
   if (rc != NIB_OK) return rc;
   if ((rc = trtri_attrs()) != NIB_OK) return rc;
-  trtri64_batched_kernel<<<ceil_div(n, NB), 256, TRTRI_SMEM, st>>>(L, ldl, n, g_dinv);
+  trtri64_batched_kernel<<<ceil_div(n, NB), 256, TRTRI_SMEM, st>>>(L, ldl, n, dinv);
   NIB_LAUNCH_CHECK();
-  if (nrhs == 1 && ldb == 1) return trsv_impl(L, n, ldl, B, trans, g_dinv, st);
-  return trsm_rec(L, ldl, B, nrhs, ldb, 0, n, trans, g_dinv, st);
+  if (nrhs == 1 && ldb == 1) return trsv_impl(L, n, ldl, B, trans, dinv, st);
+  return trsm_rec(L, ldl, B, nrhs, ldb, 0, n, trans, dinv, st);
 }
 
 
@@ -931,7 +921,7 @@ static int syrk_part(double* Kx, int ld, int r0, int M, int cc0, int N, int c0, 
   return dgemm_sub(g, st);
 }
 
-static int chol_lookahead(double* Kx, int n, int ld, int* info, cudaStream_t st) {
+static int chol_lookahead(double* Kx, int n, int ld, int* info, double* g_dinv, cudaStream_t st) {
   if (!g_chol_side) {
     NIB_CUDA(cudaStreamCreateWithFlags(&g_chol_side, cudaStreamNonBlocking));
     NIB_CUDA(cudaEventCreateWithFlags(&g_chol_ev_diag, cudaEventDisableTiming));
@@ -1041,17 +1031,13 @@ colreduce_final_kernel(const double* __restrict__ partial, int slices, int m, do
     out[j] = acc;
   }
 }
-static double* g_cr = nullptr;
-static size_t g_cr_cap = 0;
 static int colreduce(const double* V, long long ldv, int n, int m, const double* x, int mode, double* out, int var_mode,
                      double prior_var, double y_std, double* sd, cudaStream_t st) {
   const int slices = ceil_div(n, CR_ROWS);
   const size_t need = (size_t)slices * m;
-  if (g_cr_cap < need) {
-    if (g_cr) cudaFree(g_cr);
-    g_cr_cap = need < ((size_t)1 << 21) ? ((size_t)1 << 21) : need;
-    NIB_CUDA(cudaMalloc(&g_cr, g_cr_cap * sizeof(double)));
-  }
+  double* g_cr = nullptr;
+  int rcs = stream_scratch(SCRATCH_GP_COLREDUCE, st, need * sizeof(double), ((size_t)1 << 21) * sizeof(double), reinterpret_cast<void**>(&g_cr));
+  if (rcs != NIB_OK) return rcs;
   dim3 grid(ceil_div(m, 256), slices);
   colreduce_partial_kernel<<<grid, 256, 0, st>>>(V, ldv, n, m, x, mode, g_cr);
   NIB_LAUNCH_CHECK();
@@ -1189,14 +1175,9 @@ __global__ void argmax_kernel(const double* __restrict__ v, int m, long long* __
   }
 }
 
-static double* g_scratch = nullptr;  // small device scratch for scalar reductions
-static size_t g_scratch_cap = 0;
-static int ensure_scratch(size_t doubles) {
-  if (g_scratch_cap >= doubles) return NIB_OK;
-  if (g_scratch) cudaFree(g_scratch);
-  g_scratch_cap = doubles < 16384 ? 16384 : doubles;
-  NIB_CUDA(cudaMalloc(&g_scratch, g_scratch_cap * sizeof(double)));
-  return NIB_OK;
+// small device scratch for scalar reductions (per stream, common.cuh)
+static int get_scratch(size_t doubles, cudaStream_t st, double** out) {
+  return stream_scratch(SCRATCH_GP_SCALARS, st, doubles * sizeof(double), 16384 * sizeof(double), reinterpret_cast<void**>(out));
 }
 
 }  // namespace nib
@@ -1238,7 +1219,8 @@ int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   NIB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
   if (!gp_v1()) {
-    int rc = ensure_dinv(n);
+    double* g_dinv = nullptr;
+    int rc = get_dinv(n, st, &g_dinv);
     if (rc != NIB_OK) return rc;
     if ((rc = trtri_attrs()) != NIB_OK) return rc;
     static const bool rec = getenv("NIB_GP_CHOL_REC") != nullptr;   // fully recursive variant: measured slower (its
@@ -1249,7 +1231,7 @@ int nib_gp_cholesky(double* d_K, int n, int ldk, int* d_info, void* stream) {
     static const bool la = getenv("NIB_GP_LOOKAHEAD") != nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    if (la && cap == cudaStreamCaptureStatusNone) return chol_lookahead(d_K, n, ldk, d_info, st);
+    if (la && cap == cudaStreamCaptureStatusNone) return chol_lookahead(d_K, n, ldk, d_info, g_dinv, st);
     // Right-looking, two-level: 64-wide steps inside NBC-wide super-blocks.  Each step factors the diagonal block AND
     // inverts it (potrf_diag_kernel), turns the panel solve for every row below into one 64-deep product with that
     // inverse (apply_dinv_kernel) and updates the rest of the super-block's columns (rank 64); everything to the right of
@@ -1393,7 +1375,8 @@ int nib_gp_lml(const double* d_L, int n, int ldl, const double* d_y, const doubl
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(d_L && d_y && d_alpha && h_lml && n > 0, "nib_gp_lml: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ensure_scratch(16);
+  double* g_scratch = nullptr;
+  int rc = get_scratch(16, st, &g_scratch);
   if (rc != NIB_OK) return rc;
   lml_kernel<<<1, 1024, 0, st>>>(d_L, n, ldl, d_y, d_alpha, g_scratch);
   NIB_LAUNCH_CHECK();
@@ -1407,7 +1390,8 @@ int nib_gp_lml_grad(const double* d_K0, const double* d_Kinv, const double* d_al
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(d_K0 && d_Kinv && d_alpha && d_Z && h_grad && n > 0 && ld >= n, "nib_gp_lml_grad: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ensure_scratch((size_t)n + 16);
+  double* g_scratch = nullptr;
+  int rc = get_scratch((size_t)n + 16, st, &g_scratch);
   if (rc != NIB_OK) return rc;
   lml_grad_kernel<<<n, 256, 0, st>>>(d_K0, d_Kinv, d_alpha, d_Z, words, n, ld, g_scratch + 16);
   NIB_LAUNCH_CHECK();
@@ -1426,7 +1410,8 @@ int nib_gp_lml_grad_rbf(const double* d_K0, const double* d_Kinv, const double* 
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(d_K0 && d_Kinv && d_alpha && d_X && h_grad && n > 0 && d > 0 && ld >= n, "nib_gp_lml_grad_rbf: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ensure_scratch((size_t)n + 16);
+  double* g_scratch = nullptr;
+  int rc = get_scratch((size_t)n + 16, st, &g_scratch);
   if (rc != NIB_OK) return rc;
   lml_grad_rbf_kernel<<<n, 256, 0, st>>>(d_K0, d_Kinv, d_alpha, d_X, d, n, ld, 1.0 / length_scale, g_scratch + 16);
   NIB_LAUNCH_CHECK();

@@ -19,6 +19,8 @@ struct ConvParams {
   int res_cstride, res_coff, res_C;
   int R, S, stride, pad;
   int relu;
+  const int* dyn_n;     // optional device int: live image count (<= M / (P*Q)); rows of the images beyond it are skipped
+                        // by the CUDA-core kernels (the fp32 tie re-score runs on a device-side count, score.cu)
 };
 
 struct PoolParams {
@@ -29,19 +31,20 @@ struct PoolParams {
   int kind, N, Hin, Win, C, in_cstride, in_coff;
   int P, Q, out_cstride, out_coff;
   int k, stride, pad;
+  const int* dyn_n;     // as ConvParams::dyn_n
 };
 
 int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st);
 int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st);
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
-              int Cout, float* logits, cudaStream_t st);
+              int Cout, float* logits, const int* dyn_n, cudaStream_t st);
 int launch_bnrelu_pack(const void* x, int in_cstride, int in_coff, int Cin, int Cpad, const float* scale,
                        const float* shift, void* y, long long M, cudaStream_t st);
 int launch_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* out, int cs, int halo, bool bf16,
                         cudaStream_t st);
 int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int halo, bool bf16, float* out,
                         cudaStream_t st);
-int mask_synth_impl(const nib_mask_args* a, cudaStream_t st);
+int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo);
 
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ---------------------------------------------
 struct TcConvPlan;  // opaque: tensor maps + tile configuration for one conv layer

@@ -39,10 +39,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // fl(v*255) is monotone in v, so the extreme of a kept segment is fl(seg_extreme*255); removed
 // pixels contribute v*0 = 0 (v >= 0 after the a1 rescale).  max(m - mn) = fl(max(m) - mn) by
 // monotonicity of fl(x - c).
-__global__ void mask_stats_kernel(const float* __restrict__ seg_minmax, const uint64_t* __restrict__ sel,
-                                  int words, int N, int S, float2* __restrict__ stats) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// Computed inside mask_synth_kernel for the CTA's own slice of masks (shared memory): no scratch buffer is shared between
+// launches, so forwards running on different streams cannot see each other's statistics.
+__device__ __forceinline__ float2 mask_stats(const float* __restrict__ seg_minmax, const uint64_t* __restrict__ sel,
+                                             int words, int n, int S) {
   float mn = INFINITY, mx = -INFINITY;
   bool any_removed = false, any = false;
   for (int s = 0; s < S; ++s) {
@@ -62,7 +62,7 @@ __global__ void mask_stats_kernel(const float* __restrict__ seg_minmax, const ui
     mx = fmaxf(mx, 0.0f);
   }
   if (!any) { mn = 0.f; mx = 0.f; }
-  stats[n] = make_float2(mn, __fsub_rn(mx, mn));
+  return make_float2(mn, __fsub_rn(mx, mn));
 }
 
 template <int MODE>
@@ -84,11 +84,14 @@ template <typename OutT, int LAYOUT, int MODE, int VEC, typename LabT>
 __global__ void __launch_bounds__(256)
 mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels,
                   const uint64_t* __restrict__ sel, int words, int N, int C, int H, int W,
-                  const float2* __restrict__ stats, OutT* __restrict__ out, int c_stride, int pad_h,
+                  const float* __restrict__ seg_minmax, int S, OutT* __restrict__ out, int c_stride, int pad_h,
                   int pad_w, uint8_t* __restrict__ pixel_mask, int masks_per_cta) {
+  constexpr int kStatChunk = 256;   // == blockDim.x: one thread computes the (min, max - min) of one mask of the chunk
+  __shared__ float2 s_stats[MODE == NIB_MASK_REMOVE_MINMAX ? kStatChunk : 1];
   const int HW = H * W;
   const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  if (p0 >= HW) return;
+  const bool active = p0 < HW;
+  if (MODE != NIB_MASK_REMOVE_MINMAX && !active) return;   // (the REMOVE_MINMAX path has block-wide barriers below)
   const int h = p0 / W, w = p0 - h * W;
 
   int lab[VEC];
@@ -105,6 +108,16 @@ mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
 
   for (int n = n0; n < n1; ++n) {
+    if (MODE == NIB_MASK_REMOVE_MINMAX) {
+      const int k = (n - n0) % kStatChunk;
+      if (k == 0) {
+        __syncthreads();   // the previous chunk's readers are done
+        const int nn = n + (int)threadIdx.x;
+        if (nn < n1) s_stats[threadIdx.x] = mask_stats(seg_minmax, sel, words, nn, S);
+        __syncthreads();
+      }
+      if (!active) continue;
+    }
     bool bit[VEC];
     if (words == 1) {
       const uint64_t z = __ldg(sel + n);
@@ -117,7 +130,7 @@ mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels
     }
     float mn = 0.f, mxs = 1.f;
     if (MODE == NIB_MASK_REMOVE_MINMAX) {
-      float2 st = __ldg(stats + n);
+      const float2 st = s_stats[(n - n0) % kStatChunk];
       mn = st.x;
       mxs = st.y;
     }
@@ -329,7 +342,7 @@ __global__ void heat_scatter_kernel(const LabT* __restrict__ labels, int HW, int
 }
 
 template <typename OutT, int LAYOUT, int MODE, typename LabT>
-static int launch_mask(const nib_mask_args* a, const float2* stats, cudaStream_t st) {
+static int launch_mask(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
   const int HW = a->H * a->W;
   const bool vec4 = (a->W % 4 == 0);
   const int threads = 256;
@@ -343,14 +356,14 @@ static int launch_mask(const nib_mask_args* a, const float2* stats, cudaStream_t
   dim3 grid(gx, gy);
   if (vec4)
     mask_synth_kernel<OutT, LAYOUT, MODE, 4, LabT><<<grid, threads, 0, st>>>(
-        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, stats,
+        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, a->d_seg_minmax, a->S,
         (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc);
   else
     mask_synth_kernel<OutT, LAYOUT, MODE, 1, LabT><<<grid, threads, 0, st>>>(
-        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, stats,
+        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, a->d_seg_minmax, a->S,
         (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc);
   NIB_LAUNCH_CHECK();
-  if (LAYOUT == NIB_NHWC && (a->pad_h > 0 || a->pad_w > 0)) {
+  if (LAYOUT == NIB_NHWC && (a->pad_h > 0 || a->pad_w > 0) && !skip_halo) {
     const int Hp = a->H + 2 * a->pad_h, Wp = a->W + 2 * a->pad_w;
     long long total = (long long)a->N * (Hp * Wp - HW);
     halo_zero_kernel<OutT><<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
@@ -361,21 +374,19 @@ static int launch_mask(const nib_mask_args* a, const float2* stats, cudaStream_t
 }
 
 template <typename OutT, int LAYOUT, typename LabT>
-static int dispatch_mode(const nib_mask_args* a, const float2* stats, cudaStream_t st) {
-  if (a->mode == NIB_MASK_KEEP_MUL) return launch_mask<OutT, LAYOUT, NIB_MASK_KEEP_MUL, LabT>(a, stats, st);
-  return launch_mask<OutT, LAYOUT, NIB_MASK_REMOVE_MINMAX, LabT>(a, stats, st);
+static int dispatch_mode(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
+  if (a->mode == NIB_MASK_KEEP_MUL) return launch_mask<OutT, LAYOUT, NIB_MASK_KEEP_MUL, LabT>(a, skip_halo, st);
+  return launch_mask<OutT, LAYOUT, NIB_MASK_REMOVE_MINMAX, LabT>(a, skip_halo, st);
 }
 template <typename OutT, typename LabT>
-static int dispatch_layout(const nib_mask_args* a, const float2* stats, cudaStream_t st) {
-  if (a->layout == NIB_NCHW) return dispatch_mode<OutT, NIB_NCHW, LabT>(a, stats, st);
-  return dispatch_mode<OutT, NIB_NHWC, LabT>(a, stats, st);
+static int dispatch_layout(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
+  if (a->layout == NIB_NCHW) return dispatch_mode<OutT, NIB_NCHW, LabT>(a, skip_halo, st);
+  return dispatch_mode<OutT, NIB_NHWC, LabT>(a, skip_halo, st);
 }
 
-// scratch for per-mask stats, grown on demand (per process; stream-ordered use)
-static float2* g_stats = nullptr;
-static int g_stats_cap = 0;
-
-int mask_synth_impl(const nib_mask_args* a, cudaStream_t st) {
+// skip_halo: the caller guarantees the halo ring of d_out already holds +0 (the network's own input buffer is zeroed
+// when it is allocated and nothing else ever writes its halo), so it is not re-written on every forward.
+int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo) {
   NIB_REQUIRE(a != nullptr, "nib_mask_synth: null args");
   if (a->N == 0) return NIB_OK;  // an empty batch is legal (and its tensors have null data pointers)
   NIB_REQUIRE(a->d_img && a->d_labels && a->d_sel && a->d_out, "nib_mask_synth: null device pointer");
@@ -390,24 +401,14 @@ int mask_synth_impl(const nib_mask_args* a, cudaStream_t st) {
   if (a->layout == NIB_NHWC)
     NIB_REQUIRE(a->c_stride >= a->C && a->pad_h >= 0 && a->pad_w >= 0, "nib_mask_synth: bad NHWC c_stride/pad");
   if (a->N == 0) return NIB_OK;
-  const float2* stats = nullptr;
-  if (a->mode == NIB_MASK_REMOVE_MINMAX) {
+  if (a->mode == NIB_MASK_REMOVE_MINMAX)
     NIB_REQUIRE(a->d_seg_minmax != nullptr, "nib_mask_synth: REMOVE_MINMAX needs d_seg_minmax (nib_segment_minmax)");
-    if (g_stats_cap < a->N) {
-      if (g_stats) cudaFree(g_stats);
-      g_stats_cap = max(a->N, 4096);
-      NIB_CUDA(cudaMalloc(&g_stats, sizeof(float2) * g_stats_cap));
-    }
-    mask_stats_kernel<<<ceil_div(a->N, 128), 128, 0, st>>>(a->d_seg_minmax, a->d_sel, a->sel_words, a->N, a->S, g_stats);
-    NIB_LAUNCH_CHECK();
-    stats = g_stats;
-  }
   if (a->out_dtype == NIB_F32) {
-    if (a->label_bytes == 1) return dispatch_layout<float, uint8_t>(a, stats, st);
-    return dispatch_layout<float, uint16_t>(a, stats, st);
+    if (a->label_bytes == 1) return dispatch_layout<float, uint8_t>(a, skip_halo, st);
+    return dispatch_layout<float, uint16_t>(a, skip_halo, st);
   } else {
-    if (a->label_bytes == 1) return dispatch_layout<__nv_bfloat16, uint8_t>(a, stats, st);
-    return dispatch_layout<__nv_bfloat16, uint16_t>(a, stats, st);
+    if (a->label_bytes == 1) return dispatch_layout<__nv_bfloat16, uint8_t>(a, skip_halo, st);
+    return dispatch_layout<__nv_bfloat16, uint16_t>(a, skip_halo, st);
   }
 }
 
@@ -417,7 +418,7 @@ extern "C" {
 
 int nib_mask_synth(const nib_mask_args* args, void* stream) {
   NIB_DEVICE_OR_FAIL();
-  return nib::mask_synth_impl(args, (cudaStream_t)stream);
+  return nib::mask_synth_impl(args, (cudaStream_t)stream, false);
 }
 
 int nib_segment_minmax(const float* d_img, const void* d_labels, int label_bytes, int C, int H, int W,
@@ -456,8 +457,9 @@ int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S, cons
   NIB_REQUIRE(S > 0 && S <= 4096 && sel_words * 64 >= S, "nib_heatmap: bad S/sel_words");
   NIB_REQUIRE(label_bytes == 1 || label_bytes == 2, "nib_heatmap: label_bytes must be 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
-  static double* wseg = nullptr;
-  if (!wseg) NIB_CUDA(cudaMalloc(&wseg, sizeof(double) * 4096));
+  double* wseg = nullptr;   // per-stream scratch (common.cuh): concurrent heat maps on different streams do not share it
+  int rcs = nib::stream_scratch(nib::SCRATCH_HEAT_WSEG, st, sizeof(double) * 4096, sizeof(double) * 4096, reinterpret_cast<void**>(&wseg));
+  if (rcs != NIB_OK) return rcs;
   nib::heat_weights_kernel<<<S, 256, 0, st>>>(d_sel, sel_words, d_y, N, S, wseg);
   const int HW = H * W;
   if (label_bytes == 1)

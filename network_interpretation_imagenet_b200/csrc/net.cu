@@ -56,20 +56,15 @@ struct nib_net {
   int num_classes;
   bool use_tc;
   bool use_graph;
+  const int* dyn_n;           // device-side live batch size for the CUDA-core kernels (fp32 nets), or null
   long long launches, tc_launches;
-  struct GraphKey {
-    int N, layout;
-    const void* x;
-    float* logits;
-    bool operator<(const GraphKey& o) const {
-      if (N != o.N) return N < o.N;
-      if (layout != o.layout) return layout < o.layout;
-      if (x != o.x) return x < o.x;
-      return logits < o.logits;
-    }
-  };
+  // CUDA graphs of the op list, one per batch size: the graph reads the net's own input buffer and writes the net's own
+  // logits buffer (staging the caller's input and copying the logits out happen outside it), so caller pointers are not
+  // part of the key and the cache is bounded by the number of distinct batch sizes (at most kMaxGraphs, then flushed).
+  static constexpr size_t kMaxGraphs = 8;
   struct GraphVal { cudaGraphExec_t exec; long long launches, tc_launches; };
-  std::map<GraphKey, GraphVal> graphs;
+  std::map<int, GraphVal> graphs;
+  float* graph_logits;
 };
 
 static size_t elem_size(const nib_net* n) { return n->bf16 ? 2 : 4; }
@@ -108,6 +103,8 @@ int nib_net_create(int precision, int max_batch, nib_net** out) {
   n->num_classes = 0;
   n->use_tc = true;
   n->use_graph = false;
+  n->dyn_n = nullptr;
+  n->graph_logits = nullptr;
   n->launches = n->tc_launches = 0;
   *out = n;
   return NIB_OK;
@@ -119,6 +116,7 @@ int nib_net_destroy(nib_net* net) {
   for (auto& b : net->bufs)
     if (b.ptr) cudaFree(b.ptr);
   if (net->pack_scratch) cudaFree(net->pack_scratch);
+  if (net->graph_logits) cudaFree(net->graph_logits);
   for (auto& o : net->ops) {
     if (o.d_w) cudaFree(o.d_w);
     if (o.d_w_pack) cudaFree(o.d_w_pack);
@@ -316,6 +314,7 @@ static void fill_conv_params(const nib_net* net, const NetOp& op, int N, ConvPar
   }
   p->R = d.R; p->S = d.S; p->stride = d.stride; p->pad = d.pad;
   p->relu = (d.flags & NIB_CONV_RELU) ? 1 : 0;
+  p->dyn_n = net->dyn_n;
 }
 
 // the same conv, reading the packed relu(bn(x)) scratch tensor instead of the raw channel slice
@@ -431,13 +430,14 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
       p.in_cstride = bi.C; p.in_coff = op.in_coff;
       p.P = bo.H; p.Q = bo.W; p.out_cstride = bo.C; p.out_coff = op.out_coff;
       p.k = op.k; p.stride = op.stride; p.pad = op.pad;
+      p.dyn_n = net->dyn_n;
       int rc = launch_pool(p, net->bf16, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
     } else {
       const NetBuffer& bi = net->bufs[op.fc_in];
       int rc = launch_fc(bi.ptr, bi.C, net->bf16, (const float*)op.d_w, op.d_bias, N, op.fc_cin, op.fc_cout,
-                         d_logits, st);
+                         d_logits, net->dyn_n, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
     }
@@ -475,15 +475,21 @@ int nib_net_forward(nib_net* net, const void* d_x, int x_layout, int N, float* d
     if (rc != NIB_OK) return rc;
     return run_ops(net, N, d_logits, st);
   }
-  nib_net::GraphKey key{N, x_layout, d_x, d_logits};
-  auto it = net->graphs.find(key);
+  int rc = stage_input(net, d_x, x_layout, N, st);
+  if (rc != NIB_OK) return rc;
+  if (!net->graph_logits)
+    NIB_CUDA(cudaMalloc(&net->graph_logits, sizeof(float) * (size_t)net->max_batch * (net->num_classes > 0 ? net->num_classes : 1)));
+  auto it = net->graphs.find(N);
   if (it == net->graphs.end()) {
+    if (net->graphs.size() >= nib_net::kMaxGraphs) {
+      for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
+      net->graphs.clear();
+    }
     cudaStream_t cap;
     NIB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     const long long l0 = net->launches, t0 = net->tc_launches;
     NIB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    int rc = stage_input(net, d_x, x_layout, N, cap);
-    if (rc == NIB_OK) rc = run_ops(net, N, d_logits, cap);
+    rc = run_ops(net, N, net->graph_logits, cap);
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(cap, &graph);
     if (rc != NIB_OK || ce != cudaSuccess) {
@@ -500,9 +506,10 @@ int nib_net_forward(nib_net* net, const void* d_x, int x_layout, int N, float* d
     NIB_CUDA(cudaGraphInstantiate(&val.exec, graph, 0));
     cudaGraphDestroy(graph);
     cudaStreamDestroy(cap);
-    it = net->graphs.insert({key, val}).first;
+    it = net->graphs.insert({N, val}).first;
   }
   NIB_CUDA(cudaGraphLaunch(it->second.exec, st));
+  NIB_CUDA(cudaMemcpyAsync(d_logits, net->graph_logits, sizeof(float) * (size_t)N * net->num_classes, cudaMemcpyDeviceToDevice, st));
   net->launches += it->second.launches;
   net->tc_launches += it->second.tc_launches;
   return NIB_OK;
@@ -538,7 +545,8 @@ int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flo
     const NetOp& op = net->ops[i];
     if (op.kind == 0) {
       const NetBuffer& bo = net->bufs[op.cd.out_buf];
-      h_kind[i] = (op.plan && net->use_tc) ? 1 : 0;
+      // 4: a tcgen05 conv computed by the PREVIOUS op's fused launch (its own slot only holds event overhead)
+      h_kind[i] = (op.fused_skip && net->use_tc) ? 4 : (op.plan && net->use_tc) ? 1 : 0;
       h_flops[i] = 2.0 * N * bo.H * bo.W * (double)op.cd.R * op.cd.S * op.cd.Cin * op.cd.Cout;
       if (h_geom) {
         int* g = h_geom + 8 * i;
@@ -582,8 +590,9 @@ int nib_net_forward_masked(nib_net* net, const nib_mask_args* args, float* d_log
   a.layout = NIB_NHWC;
   a.c_stride = bi.C;
   a.pad_h = a.pad_w = bi.pad;
-  int rc = mask_synth_impl(&a, (cudaStream_t)stream);
-  net->launches += 1 + (bi.pad > 0) + (a.mode == NIB_MASK_REMOVE_MINMAX);
+  // the input buffer's halo ring was zeroed by nib_net_add_buffer and no op writes it: skip the per-forward re-zeroing
+  int rc = mask_synth_impl(&a, (cudaStream_t)stream, true);
+  net->launches += 1;
   if (rc != NIB_OK) return rc;
   return nib_net_forward(net, bi.ptr, NIB_IN_NATIVE, args->N, d_logits, stream);
 }
@@ -618,6 +627,15 @@ int nib_net_launch_counts(nib_net* net, long long* total, long long* tcgen05) {
 int nib_net_set_tensor_core(nib_net* net, int enable) {
   NIB_REQUIRE(net != nullptr, "nib_net_set_tensor_core: null handle");
   net->use_tc = enable != 0;
+  for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
+  net->graphs.clear();
+  return NIB_OK;
+}
+
+int nib_net_set_dynamic_batch(nib_net* net, const int32_t* d_count) {
+  NIB_REQUIRE(net != nullptr, "nib_net_set_dynamic_batch: null handle");
+  NIB_REQUIRE(d_count == nullptr || !net->bf16, "nib_net_set_dynamic_batch: only fp32 (CUDA-core) networks honour a device-side batch size");
+  net->dyn_n = d_count;
   for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
   net->graphs.clear();
   return NIB_OK;

@@ -6,9 +6,11 @@ bayesian_active_learning_imagenet.py:178-198): instead of one mask, one H2D copy
 one device sync per iteration, all N masks of an image are synthesised and scored in micro-batches on the
 device, and each rank of a torch.distributed job scores a contiguous slice of the masks (masks are
 independent work units); one all-gather of (target_prob, top1) per call is the only
-collective.
+collective (libnib's nib_allgather_scores on NCCL; torch.distributed on CPU/gloo for the host-logic tests).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
@@ -19,10 +21,19 @@ from .classifier import Classifier
 from .masks import KEEP_MUL, REMOVE_MINMAX, MaskSynth
 from .scoring import score
 
+# Relative top-2 margin, (top1 - runner-up) / max|logit|, below which a bf16-scored mask is re-scored in fp32.
+# A bf16 arg-max can differ from the fp32 one only if the error of the DIFFERENCE of two logits exceeds their margin.
+# Measured on the bench workload (ResNet-101, 3072 masks, tests/test_gpu_bench_config.py): max |logit error| 4.8e-3 of
+# max|logit|, max error of any (top1 - other) difference 2.9e-3; the default band is that bound with a 2x safety factor,
+# well inside twice the 1e-2 logit tolerance north_star states (which, taken literally as the band, would re-score
+# every mask of a near-tied random-init network: all 3072 margins of the bench workload are below 2e-2).
+DEFAULT_TIE_BAND = 6e-3
+DEFAULT_TIE_CAPACITY = 128
+
 
 def shard_range(N: int, rank: int, world: int) -> tuple[int, int, int]:
     """Contiguous slice [lo, hi) of N masks for `rank`, and the padded per-rank length (equal on all ranks so a
-    single all_gather_into_tensor works).  Mask order is global, so results are identical to a 1-GPU run."""
+    single all-gather works).  Mask order is global, so results are identical to a 1-GPU run."""
     per = (N + world - 1) // world
     lo = min(N, rank * per)
     hi = min(N, lo + per)
@@ -30,7 +41,8 @@ def shard_range(N: int, rank: int, world: int) -> tuple[int, int, int]:
 
 
 def gather_scores(local: torch.Tensor, N: int, group=None) -> torch.Tensor:
-    """All-gather a [per, F] per-rank score block into the global [N, F] table (works on gloo/CPU and nccl/CUDA)."""
+    """All-gather a [per, F] per-rank score block into the global [N, F] table through torch.distributed (works on
+    gloo/CPU and nccl/CUDA).  The CUDA engine uses ScoreComm (libnib, NCCL from the C ABI) instead."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local[:N]
     world = dist.get_world_size(group)
@@ -39,16 +51,56 @@ def gather_scores(local: torch.Tensor, N: int, group=None) -> torch.Tensor:
     return out[:N]
 
 
+class ScoreComm:
+    """NCCL communicator owned by libnib (nib_comm_init / nib_allgather_scores).  The 128-byte unique id is created
+    by rank 0 inside the library and broadcast over the existing torch.distributed group (bootstrap only); the
+    all-gather itself is the C-ABI call on the caller's stream."""
+
+    def __init__(self, group=None, device=None):
+        self.lib = _lib.load()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _lib.check(self.lib.nib_comm_unique_id(buf), "nib_comm_unique_id")
+            ident = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        backend = dist.get_backend(group)
+        t = ident.to(device) if backend == "nccl" else ident
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        h = C.c_void_p()
+        _lib.check(self.lib.nib_comm_init(raw, self.rank, self.world, C.byref(h)), "nib_comm_init")
+        self.h = h
+
+    def allgather(self, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """local [per, 2] fp32 cuda -> out [world*per, 2] on the current stream."""
+        per = int(local.shape[0])
+        _lib.check(self.lib.nib_allgather_scores(self.h, local.data_ptr(), per, out.data_ptr(), _lib.stream_handle()),
+                   "nib_allgather_scores")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.nib_comm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class PerturbationEngine:
-    """refine_ties: relative top-2 margin (top1 - runner-up) / max|logit| below which a bf16-scored mask is
-    re-scored by an fp32 copy of the classifier.  bf16 logits agree with the reference's fp32 logits to <= 1e-2
-    relative, so a mask whose margin is inside ~3x that band could flip its arg-max; re-scoring exactly those keeps
-    top-1 identical to the reference on every mask at a cost proportional to the number of near-ties."""
+    """refine_ties: relative top-2 margin (top1 - runner-up) / max|logit| below which a bf16-scored mask is re-scored by
+    an fp32 copy of the classifier, so that top-1 equals the reference's on every mask outside numerical noise.
+    "auto" (default) = DEFAULT_TIE_BAND for bf16 classifiers lowered from a torch module, off otherwise; None/0 = off.
+    The policy runs entirely on the device (no host synchronisation): near-tie rows are compacted into a buffer of
+    `tie_capacity` rows, the fp32 network runs on that buffer with the device-side count as its live batch size, and the
+    refined scores are scattered back.  `tie_stats()` reads the counters (rows refined, rows that did not fit)."""
 
     def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
                  max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False,
-                 refine_ties: float | None = None, streams: int = 1):
-        _lib.load()
+                 refine_ties="auto", streams: int = 1, tie_capacity: int = DEFAULT_TIE_CAPACITY):
+        self.lib = _lib.load()
         self.device = torch.device(device)
         self.target = int(target)
         self.mode = mode
@@ -56,44 +108,128 @@ class PerturbationEngine:
         self.synth = MaskSynth(image, segments, S=S, device=device)
         self.classifier = model if isinstance(model, Classifier) else Classifier.from_torch(
             model, (self.synth.H, self.synth.W), precision=precision, max_batch=max_batch, streams=streams)
-        self.refine_ties = refine_ties if self.classifier.precision == "bf16" else None
         self._model_src = None if isinstance(model, Classifier) else model
-        self._fp32 = None
-        self.refined = 0
+        if isinstance(refine_ties, str):
+            if refine_ties != "auto":
+                raise ValueError("refine_ties must be 'auto', None or a float")
+            refine_ties = DEFAULT_TIE_BAND if (self.classifier.precision == "bf16" and self._model_src is not None) else None
+        self.refine_ties = float(refine_ties) if (refine_ties and self.classifier.precision == "bf16") else None
         if self.refine_ties is not None and self._model_src is None:
             raise ValueError("refine_ties needs the torch module (to lower an fp32 copy), not a lowered Classifier")
+        self.tie_capacity = int(tie_capacity)
+        self._fp32 = None
+        self._tie = None
+        self._calls = 0
         if use_graph:
             self.classifier.set_graph(True)
         self.rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._comm = None
+        self._bufs: dict = {}
 
+    # -- tie policy ------------------------------------------------------------------------------------
     def _fp32_classifier(self) -> Classifier:
         if self._fp32 is None:
             self._fp32 = Classifier.from_torch(self._model_src, (self.synth.H, self.synth.W), precision="fp32",
-                                               max_batch=min(self.classifier.max_batch, 64))
+                                               max_batch=self.tie_capacity)
         return self._fp32
 
-    def score_local(self, sel_bits, out: torch.Tensor | None = None):
-        """Scores for the given selections on this rank only.  Returns [n, 2] fp32: (target_prob, top1)."""
-        d_sel = self.synth.device_bits(sel_bits)
+    def _tie_state(self):
+        if self._tie is None:
+            dev, cap = self.device, self.tie_capacity
+            f32 = self._fp32_classifier()
+            t = {"idx": torch.full((cap,), -1, dtype=torch.int32, device=dev),
+                 "sel": torch.zeros(cap, self.synth.words, dtype=torch.int64, device=dev),
+                 "count": torch.zeros(1, dtype=torch.int32, device=dev),
+                 "logits": torch.zeros(cap, f32.num_classes, dtype=torch.float32, device=dev),
+                 "totals": torch.zeros(2, dtype=torch.int64, device=dev)}   # (near-ties, did not fit), read by tie_stats()
+            t["score"] = {"top1": torch.empty(cap, dtype=torch.int32, device=dev),
+                          "target_prob": torch.empty(cap, dtype=torch.float32, device=dev),
+                          "max_prob": torch.empty(cap, dtype=torch.float32, device=dev),
+                          "correct": torch.empty(cap, dtype=torch.uint8, device=dev),
+                          "margin": torch.empty(cap, dtype=torch.float32, device=dev)}
+            _lib.check(self.lib.nib_net_set_dynamic_batch(f32.h, t["count"].data_ptr()), "nib_net_set_dynamic_batch")
+            self._tie = t
+        return self._tie
+
+    def _refine(self, d_sel: torch.Tensor, s: dict, table: torch.Tensor | None, synth: MaskSynth):
+        """Device-side tie policy on the scores `s` of the rows `d_sel` (no host sync)."""
+        t = self._tie_state()
+        n, cap = int(d_sel.shape[0]), self.tie_capacity
+        st = _lib.stream_handle()
+        _lib.check(self.lib.nib_tie_compact(s["margin"].data_ptr(), n, self.refine_ties, d_sel.data_ptr(), self.synth.words,
+                                            cap, t["idx"].data_ptr(), t["sel"].data_ptr(), t["count"].data_ptr(),
+                                            t["totals"].data_ptr(), st), "nib_tie_compact")
+        f32 = self._fp32_classifier()
+        f32.forward_masked(synth, t["sel"], self.mode, out=t["logits"])
+        score(t["logits"], self.target, out=t["score"])
+        r = t["score"]
+        _lib.check(self.lib.nib_tie_scatter(t["idx"].data_ptr(), t["count"].data_ptr(), cap, r["top1"].data_ptr(),
+                                            r["target_prob"].data_ptr(), r["max_prob"].data_ptr(), r["correct"].data_ptr(),
+                                            s["top1"].data_ptr(), s["target_prob"].data_ptr(), s["max_prob"].data_ptr(),
+                                            s["correct"].data_ptr(), table.data_ptr() if table is not None else None, st),
+                   "nib_tie_scatter")
+
+    def tie_stats(self) -> dict:
+        """Counters of the tie policy since construction (one host read)."""
+        if self._tie is None:
+            return {"band": self.refine_ties, "capacity": self.tie_capacity, "calls": self._calls, "near_ties": 0, "overflow": 0}
+        found, over = (int(v) for v in self._tie["totals"].tolist())
+        return {"band": self.refine_ties, "capacity": self.tie_capacity, "calls": self._calls, "near_ties": found,
+                "refined": found - over, "overflow": over}
+
+    @property
+    def refined(self) -> int:
+        st = self.tie_stats()
+        return st.get("refined", 0)
+
+    # -- scoring ---------------------------------------------------------------------------------------
+    def _scratch(self, n: int) -> dict:
+        b = self._bufs.get(n)
+        if b is None:
+            dev = self.device
+            b = {"logits": torch.empty(n, self.classifier.num_classes, dtype=torch.float32, device=dev),
+                 "top1": torch.empty(n, dtype=torch.int32, device=dev),
+                 "target_prob": torch.empty(n, dtype=torch.float32, device=dev),
+                 "max_prob": torch.empty(n, dtype=torch.float32, device=dev),
+                 "correct": torch.empty(n, dtype=torch.uint8, device=dev),
+                 "margin": torch.empty(n, dtype=torch.float32, device=dev)}
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            self._bufs[n] = b
+        return b
+
+    def score_local(self, sel_bits, out: torch.Tensor | None = None, synth: MaskSynth | None = None):
+        """Scores for the given selections on this rank only.  Returns [n, 2] fp32: (target_prob, top1).  No host
+        synchronisation: mask synthesis, forward, scoring (which writes the table directly) and the tie policy are all
+        queued on the current stream.  `synth`: another image + label map of the same geometry (sweeps over many
+        images share one lowered classifier, BASELINE configs[4])."""
+        synth = self.synth if synth is None else synth
+        d_sel = synth.device_bits(sel_bits)
         n = int(d_sel.shape[0])
         if out is None:
             out = torch.zeros(n, 2, dtype=torch.float32, device=self.device)
         if n == 0:
             return out
-        logits = self.classifier.forward_masked(self.synth, d_sel, self.mode)
-        s = score(logits, self.target)
-        out[:n, 0] = s["target_prob"]
-        out[:n, 1] = s["top1"].to(torch.float32)   # class ids < 2^24 are exact in fp32
+        self._calls += 1
+        b = self._scratch(n)
+        self.classifier.forward_masked(synth, d_sel, self.mode, out=b["logits"])
+        s = score(b["logits"], self.target, out=b, table=out[:n])
         if self.refine_ties is not None:
-            idx = torch.nonzero(s["margin"] < self.refine_ties).flatten()   # one host sync per call
-            if idx.numel() > 0:
-                self.refined += int(idx.numel())
-                lg = self._fp32_classifier().forward_masked(self.synth, d_sel[idx], self.mode)
-                s2 = score(lg, self.target)
-                out[idx, 0] = s2["target_prob"]
-                out[idx, 1] = s2["top1"].to(torch.float32)
+            self._refine(d_sel, s, out[:n], synth)
         return out
+
+    def gather(self, local: torch.Tensor, N: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Global [N, 2] table from the per-rank [per, 2] blocks."""
+        if self.world == 1:
+            return local[:N]
+        if local.is_cuda and dist.get_backend(self.group) == "nccl":
+            if self._comm is None:
+                self._comm = ScoreComm(self.group, self.device)
+            if out is None:
+                out = torch.empty(self.world * local.shape[0], 2, dtype=torch.float32, device=local.device)
+            return self._comm.allgather(local, out)[:N]
+        return gather_scores(local, N, self.group)
 
     def score_masks(self, sel_bits) -> dict:
         """All N masks, sharded over the ranks of `group`; every rank returns the full tables."""
@@ -102,6 +238,6 @@ class PerturbationEngine:
         lo, hi, per = shard_range(N, self.rank, self.world)
         local = torch.zeros(per, 2, dtype=torch.float32, device=self.device)
         self.score_local(bits[lo:hi], out=local)
-        table = gather_scores(local, N, self.group)
+        table = self.gather(local, N)
         top1 = table[:, 1].to(torch.int32)
         return {"target_prob": table[:, 0], "top1": top1, "correct": (top1 == self.target)}

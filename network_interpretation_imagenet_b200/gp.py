@@ -118,6 +118,7 @@ class GaussianProcessRegressor:
         self.alpha_vec = torch.empty(n, dtype=torch.float64, device=dev)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         self._K0 = self._Kinv = None
+        self._fitted = False
 
         if self.optimizer is not None:
             lo, hi = np.log(self.length_scale_bounds[0]), np.log(self.length_scale_bounds[1])
@@ -143,11 +144,22 @@ class GaussianProcessRegressor:
             self.length_scale_ = self.length_scale0
         self._factor(self.length_scale_)
         self._K0 = self._Kinv = None   # free optimiser scratch
+        self._fitted = True
         return self
 
     def log_marginal_likelihood(self, theta=None, eval_gradient: bool = False, _keep: bool = True):
-        """_gpr.py:538-655 for theta = log(length_scale)."""
+        """_gpr.py:538-655 for theta = log(length_scale).  Side-effect free like scikit-learn's: the factor lives in
+        the model's own L / alpha buffers (no second n x n allocation), so a query at another theta on a fitted model
+        (`_keep`, the default; `fit` passes False while it searches) re-factors at the fitted length scale afterwards."""
         ell = self.length_scale_ if theta is None else float(np.exp(np.atleast_1d(theta)[0]))
+        restore = _keep and getattr(self, "_fitted", False) and ell != self.length_scale_
+        try:
+            return self._lml(ell, eval_gradient)
+        finally:
+            if restore:
+                self._factor(self.length_scale_)
+
+    def _lml(self, ell: float, eval_gradient: bool):
         n = self.n
         st = _lib.stream_handle()
         self.stats["lml_evals"] += 1

@@ -93,15 +93,18 @@ def test_imagenet_config_end_to_end_bf16(nib):
     sels = nib.draw_selections("subset_keep", 50, 24, seed=1)
     target = int(ocls.forward_logits(model, x[None]).argmax(1)[0])
     (top1, tprob, _, _), logits = _oracle_loop(model, x, seg, sels, "keep", target)
-    eng = nib.PerturbationEngine(model, x, seg, target, mode=nib.KEEP_MUL, precision="bf16", max_batch=16, S=50,
-                                 refine_ties=0.03)
+    eng = nib.PerturbationEngine(model, x, seg, target, mode=nib.KEEP_MUL, precision="bf16", max_batch=16, S=50)
+    assert eng.refine_ties is not None                          # the tie policy is on by default in bf16
     bits = nib.selection_bits(sels, 50)
     got_logits = eng.classifier.forward_masked(eng.synth, bits, nib.KEEP_MUL).cpu().numpy()
-    err = np.abs(got_logits - logits).max() / np.abs(logits).max()
+    err = (np.abs(got_logits - logits) / np.abs(logits).max(axis=1, keepdims=True)).max()
     assert err <= 1e-2, err
     out = eng.score_masks(bits)
     assert np.array_equal(out["top1"].cpu().numpy(), top1)      # identical top-1 on every mask (ties re-scored in fp32)
-    np.testing.assert_allclose(out["target_prob"].cpu().numpy(), tprob, rtol=0.1, atol=1e-4)
+    # |d ln p| <= 2 * (logit tolerance) * max|logit|: the bound the 1e-2 logit tolerance implies for a softmax probability
+    rtol = float(np.expm1(2 * 1e-2 * np.abs(logits).max()))
+    p = out["target_prob"].cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(p - tprob) <= rtol * tprob), (float((np.abs(p - tprob) / tprob).max()), rtol)
 
 
 def test_densenet121_tie_refinement_gives_identical_top1(nib):
@@ -116,6 +119,47 @@ def test_densenet121_tie_refinement_gives_identical_top1(nib):
                                  refine_ties=0.05)
     out = eng.score_masks(nib.selection_bits(sels, 50))
     assert np.array_equal(out["top1"].cpu().numpy(), top1), (eng.refined, out["top1"].cpu().numpy(), top1)
+
+
+def test_cifar_bf16_with_tie_policy_gives_identical_top1_on_every_mask(nib):
+    """ResNet-56 in bf16 sits outside the 1e-2 logit tolerance (tests/test_gpu_classifier.py), so its tie band is wider:
+    masks whose top-2 margin is inside it are re-scored by the fp32 lowering and top-1 equals the oracle's on all 192."""
+    raw = synthetic.synthetic_image("cifar")
+    seg = synthetic.voronoi_labels(32, 32, 20, seed=11)
+    org, _ = om.prep_minmax_u8(raw)
+    model = ocls.load_resnet56()
+    sels = nib.draw_selections("cifar", 20, 192, seed=7)
+    target = int(ocls.forward_logits(model, raw[None]).argmax(1)[0])
+    (top1, tprob, _, corr), logits = _oracle_loop(model, org, seg, sels, "remove", target)
+    d_org, _ = nib.prep_minmax_u8(raw)
+    eng = nib.PerturbationEngine(model, d_org, seg, target, mode=nib.REMOVE_MINMAX, precision="bf16", max_batch=64, S=20,
+                                 refine_ties=0.08, tie_capacity=192)
+    out = eng.score_masks(nib.selection_bits(sels, 20))
+    st = eng.tie_stats()
+    assert st["overflow"] == 0, st
+    assert np.array_equal(out["top1"].cpu().numpy(), top1), st
+    assert np.array_equal(out["correct"].cpu().numpy().astype(np.uint8), corr)
+
+
+def test_many_tiny_forwards_on_four_streams_match_one_stream(nib):
+    """Stress for scratch shared between streams: 400 masks in micro-batches of 4 over 4 stream copies in
+    REMOVE_MINMAX mode - per-mask statistics, segment min/max and the activation buffers of neighbouring micro-batches
+    are all in flight at once - must reproduce the single-stream scores bit for bit, several times over."""
+    raw = synthetic.synthetic_image("mnist")
+    seg = synthetic.voronoi_labels(28, 28, 16, seed=11)
+    model = ocls.load_mnist_net()
+    sels = nib.draw_selections("mnist", 16, 400, seed=9)
+    bits = nib.selection_bits(sels, 16)
+    d_org, _ = nib.prep_minmax_u8(raw)
+    ref = None
+    for streams in (1, 4, 4, 4):
+        eng = nib.PerturbationEngine(model, d_org, seg, 3, mode=nib.REMOVE_MINMAX, precision="fp32", max_batch=4, S=16,
+                                     streams=streams)
+        o = eng.score_masks(bits)
+        cur = (o["target_prob"].cpu().numpy(), o["top1"].cpu().numpy())
+        if ref is None:
+            ref = cur
+        assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1])
 
 
 def test_two_rank_sharding_matches_single_gpu(nib):

@@ -98,6 +98,52 @@ def test_sizes_vs_oracle(nib, n, m, S):
         np.testing.assert_allclose(g1[0], g0, rtol=1e-6, atol=1e-8)
 
 
+def test_n8192_vs_oracle(nib):
+    """BASELINE configs[3] size, n = m = 8192: the 512-wide Cholesky super-blocks and the recursive TRSM (which only engage
+    at large n) against the scikit-learn-pinned oracle (scipy cholesky / solve_triangular on the host, ~20 s)."""
+    n = m = 8192
+    S, ell = 50, 3.0
+    rng = np.random.RandomState(8192)
+    sels = [list(rng.choice(S - 1, size=20, replace=False)) for _ in range(n + m)]
+    Z = om.selection_bits(sels, S)
+    X = ogp.bits_to_matrix(Z, S)
+    y = rng.rand(n)
+    fit = ogp.gp_fit(X[:n], y, ell)
+    mu0, var0, sd0 = ogp.gp_predict(fit, X[n:])
+    gp = nib.GaussianProcessRegressor(alpha=1e-5, length_scale=ell, optimizer=None, query_chunk=8192)
+    gp.fit(Z[:n], y)
+    mu, var, sd = (t.cpu().numpy() for t in gp.predict_device(Z[n:]))
+    assert np.abs(mu - mu0).max() <= TOL, np.abs(mu - mu0).max()
+    assert np.abs(var - var0).max() <= TOL, np.abs(var - var0).max()
+    L = torch.tril(gp.L).cpu().numpy()
+    assert np.abs(L - fit["L"]).max() <= 1e-7, np.abs(L - fit["L"]).max()
+    np.testing.assert_allclose(gp.alpha_vec.cpu().numpy(), fit["alpha"], rtol=1e-5, atol=1e-5 * np.abs(fit["alpha"]).max())
+    ei, arg = nib.expected_improvement_device(torch.from_numpy(mu).cuda(), torch.from_numpy(sd).cuda(), float(y.max()), True)
+    ref_ei = -ogp.expected_improvement(mu0, sd0, y, greater_is_better=True)
+    assert int(arg.item()) == int(np.nanargmax(ref_ei))
+
+
+def test_log_marginal_likelihood_leaves_the_fitted_model_untouched(nib):
+    """scikit-learn's log_marginal_likelihood(theta) is side-effect free (_gpr.py:538-655): querying another theta on a
+    fitted model must not change what predict() returns (it used to overwrite L and alpha in place)."""
+    S, n, m = 50, 300, 64
+    rng = np.random.RandomState(5)
+    sels = [list(rng.choice(S - 1, size=20, replace=False)) for _ in range(n + m)]
+    Z = om.selection_bits(sels, S)
+    y = rng.rand(n)
+    gp = nib.GaussianProcessRegressor(alpha=1e-5, length_scale=3.0, optimizer=None).fit(Z[:n], y)
+    mu_a, sd_a = gp.predict(Z[n:], return_std=True)
+    lml_fit = gp.log_marginal_likelihood()
+    lml_other, g = gp.log_marginal_likelihood(np.log([0.7]), eval_gradient=True)
+    assert lml_other != lml_fit
+    mu_b, sd_b = gp.predict(Z[n:], return_std=True)
+    assert np.array_equal(mu_a, mu_b) and np.array_equal(sd_a, sd_b)
+    assert gp.log_marginal_likelihood() == lml_fit
+    lml0, g0 = ogp.lml_and_grad(ogp.bits_to_matrix(Z[:n], S), (y - y.mean()) / y.std(), 0.7)
+    np.testing.assert_allclose(lml_other, lml0, rtol=1e-8)
+    np.testing.assert_allclose(g[0], g0, rtol=1e-6, atol=1e-8)
+
+
 def test_duplicate_masks_without_jitter_raise_like_sklearn(nib):
     Z = om.selection_bits([[1, 2, 3], [1, 2, 3], [4, 5]], 50)
     gp = nib.GaussianProcessRegressor(alpha=0.0, length_scale=1.0, optimizer=None)

@@ -64,7 +64,7 @@ def test_abi_exports_every_declared_symbol(nib):
     for name in sorted(declared):
         assert hasattr(lib, name), f"libnib.so does not export {name}"
     assert declared == set(nib._lib.EXPORTED_SYMBOLS), declared ^ set(nib._lib.EXPORTED_SYMBOLS)
-    assert lib.nib_abi_version() == 1
+    assert lib.nib_abi_version() == nib._lib.ABI_VERSION == int(re.search(r"#define NIB_ABI_VERSION (\d+)", hdr).group(1))
 
 
 def test_compute_fails_loudly_without_a_gpu(nib):
