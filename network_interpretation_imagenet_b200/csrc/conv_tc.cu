@@ -10,12 +10,12 @@
 // Both land as a 128 x 64 bf16, 128B-swizzled, K-major tile = one tcgen05.mma operand.
 // Weights are KRSC ([Cout][R*S*Cin], BN folded) and arrive through a second tiled map.
 //
-// Four kernels live in this file, oldest first: conv_tc_kernel (v1, described next; still serves Cout = 32 tiles and the
-// fp32-output GEMM self-test), conv_tc2_kernel (v2: persistent, TMA-store epilogue), conv_tc3_kernel (v3, the default: CTA
-// pairs with tcgen05 cta_group::2) and conv_fused_ca_kernel (a 1x1 expansion + the next 1x1 reduction in one launch).
-// DESIGN.md section 4 has the measurements that led from one to the next.
+// Three kernels live in this file: conv_tc_kernel (one CTA per tile, described next; serves Cout = 32 tiles and the
+// fp32-output GEMM self-test), conv_tc3_kernel (the default: persistent CTA pairs with tcgen05 cta_group::2) and
+// conv_fused_ca_kernel (a 1x1 expansion + the next 1x1 reduction in one launch).  DESIGN.md section 4 has the
+// measurements that led from one to the next (an intermediate one-CTA persistent generation was removed in round 2).
 //
-// v1: CTA = 192 threads, warp-specialised:  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
+// conv_tc_kernel: CTA = 192 threads, warp-specialised:  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
 // (warp 1 also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> bias /
 // residual / ReLU -> bf16 -> global).  The accumulator (128 lanes x BLOCK_N fp32 columns) lives
 // in TMEM; smem holds a STAGES-deep ring of (A, B) tiles guarded by full/empty mbarriers.
@@ -58,19 +58,8 @@ struct TcKernelParams {
   int in_coff;
   int n_tiles;      // ceil(Cout / BLOCK_N)
   int m_tiles;      // ceil(M / tile_rows)
-  int pf_dist;      // v2: L2-prefetch the operands of the tile this many iterations ahead (0 = off)
   unsigned int* err_flag;
   unsigned long long* dbg;   // NIB_TC_DBG=1: per-CTA role timers (cycles), 16 slots per CTA; null in production
-  // v3 L2 prefetch by the (mostly idle) epilogue warps: the activation rows / residual rows of the tile this CTA will
-  // work on two tiles from now, so the producer's TMA loads hit L2 instead of paying the DRAM round trip with a ring
-  // that holds well under one tile.  1x1 stride-1 layers only (rows are contiguous channel vectors).
-  int m_rev;                 // v3: walk the M tiles from the last to the first (serpentine order across layers: a layer that
-                             // starts where its producer finished finds the most recently written rows still in L2)
-  int k_rot;                 // v3: CTA pair i starts its K loop at block (i * k_rot) % num_k_blocks (0: everyone at block 0)
-  const char* pf_a;          // first byte of the activation matrix slice (row 0, channel in_coff); null: off
-  long long pf_a_pitch;      // bytes between rows
-  int pf_a_lines;            // 128 B lines per row (Cin * 2 / 128)
-  long long pf_res_pitch;    // residual rows (p.res + res_coff is row 0)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -126,21 +115,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// L2 prefetch of a future tile's operands: with one CTA per SM the smem ring holds < 1 tile of a K=256 layer, so a
-// DRAM-latency load (~3 us measured under load) throttles the ring to ring_bytes / latency.  Prefetching tiles that
-// are `pf_dist` iterations ahead into L2 turns those into L2-hit loads without spending shared memory.
+// L2 prefetch of a tile the kernel will TMA-load a little later (the fused kernel's next residual chunk)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* tm, int c, int w, int h, int n, uint16_t off_w,
-                                                       uint16_t off_h) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -392,41 +370,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
-// =====================================================================================================
-// v2: persistent kernel.  One CTA per SM loops over output tiles (n-tile fastest so the CTAs that share an
-// A tile run together and hit L2).  Differences from v1 that matter for the memory-heavy layers (1x1
-// expansions with residual, K = 64..256, where the epilogue — not the MMA — is the critical path):
-//   * accumulators are double-buffered in TMEM (2 x BLOCK_N columns): the MMA issuer starts tile i+1 while
-//     the epilogue warps drain tile i;
-//   * the residual tile is prefetched by the TMA producer into (double-buffered) swizzled smem while the
-//     main loop runs, instead of 64-byte strided global loads per lane;
-//   * the output goes registers -> swizzled smem box (128 rows x 64 channels) -> one TMA store per box:
-//     full 128 B lines instead of 32 sectors per store request (profiles/r01_ncu_conv_tc_v1_layer3.csv).
-static constexpr int TC2_EPI_WGS = 2;                         // epilogue warpgroups (one per TMEM accumulator buffer)
-static constexpr int TC2_THREADS = 64 + 128 * TC2_EPI_WGS;    // producer warp + MMA warp + epilogue warps
-static constexpr int TC2_BRES_KBLOCKS = 9;                    // resident-weights mode: up to 9 k-blocks (3x3 x 64 ch)
-
-// BRES: the whole weight matrix of the layer (Cout == BLOCK_N, <= 9 k-blocks) is loaded once per CTA and stays in
-// smem for every tile; the ring then carries A tiles only.  For the 64-channel layers (stem, 56x56 3x3) the
-// per-tile weight re-fetch was the dominant L2 -> SM traffic.
-template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES>
-struct Tc2Smem {
-  static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + (BRES ? 0 : B_BYTES);
-  static constexpr int NBOX = BLOCK_N / 64;
-  static constexpr int BOX_BYTES = TC_BLOCK_M * 128;
-  static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BRES_BYTES = BRES ? TC2_BRES_KBLOCKS * B_BYTES : 0;
-  static constexpr int RES_OFFSET = BRES_OFFSET + BRES_BYTES;
-  static constexpr int RES_BYTES = HAS_RES ? 2 * NBOX * BOX_BYTES : 0;
-  static constexpr int OUT_OFFSET = RES_OFFSET + RES_BYTES;
-  static constexpr int OUT_BYTES = TC2_EPI_WGS * BOX_BYTES;   // one store-staging box per epilogue warpgroup
-  static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 9;
-  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
-};
-
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -439,7 +382,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -449,278 +391,12 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES>
-__global__ void __launch_bounds__(TC2_THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                const TcKernelParams p) {
-  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + SM::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
-  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  auto res_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
-  auto res_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
-  const uint32_t bres_full_bar = bar_base + 8u * (2 * STAGES + 8);
-  const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  auto res_box = [&](int buf, int b) { return smem_base + SM::RES_OFFSET + (uint32_t)(buf * SM::NBOX + b) * SM::BOX_BYTES; };
-  auto out_box = [&](int buf) { return smem_base + SM::OUT_OFFSET + (uint32_t)buf * SM::BOX_BYTES; };
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  constexpr bool has_res = HAS_RES;
-  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-    prefetch_tmap(&tmOut);
-    if (has_res) prefetch_tmap(&tmRes);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), 4);
-      mbar_init(res_full_bar(b), 1);
-      mbar_init(res_empty_bar(b), 4);
-    }
-    mbar_init(bres_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      if (BRES) {   // the layer's whole weight matrix, once
-        mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(p.num_k_blocks * SM::B_BYTES));
-        for (int kb = 0; kb < p.num_k_blocks; ++kb)
-          tma_load_2d(smem_base + SM::BRES_OFFSET + kb * SM::B_BYTES, &tmB, bres_full_bar, kb * TC_BLOCK_K, 0);
-      }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int m0 = m_tile * p.tile_rows;
-        const int n0 = n_tile * BLOCK_N;
-        if (p.pf_dist > 0) {
-          const int ft = tile + p.pf_dist * (int)gridDim.x;
-          if (ft < total_tiles) {
-            const int fn = ft % p.n_tiles, fm = ft / p.n_tiles;
-            const int fm0 = fm * p.tile_rows;
-            if (has_res) {
-#pragma unroll
-              for (int b = 0; b < SM::NBOX; ++b) tma_prefetch_2d(&tmRes, p.res_coff + fn * BLOCK_N + 64 * b, fm0);
-            }
-            // the A tile is shared by the n_tiles CTAs working on the same rows: one of them prefetches it
-            if (fn == 0 || p.n_tiles > (int)gridDim.x) {
-              if (p.im2col == 1) {
-                const int pq = p.P * p.Q;
-                const int fi = fm0 / pq, rem = fm0 - fi * pq;
-                const int pp = rem / p.Q, qq = rem - pp * p.Q;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                  const int tap = kb / p.cblocks;
-                  const int r = tap / p.S, sx = tap - r * p.S;
-                  tma_prefetch_im2col_4d(&tmA, (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff, qq * p.stride - p.pad,
-                                         pp * p.stride - p.pad, fi, (uint16_t)sx, (uint16_t)r);
-                }
-              } else if (p.im2col == 2) {
-                const int fi = fm / p.P;
-                const int fh = (fm - fi * p.P) * p.stride;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_prefetch_4d(&tmA, 0, 0, fh + kb, fi);
-              } else {
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_prefetch_2d(&tmA, kb * TC_BLOCK_K + p.in_coff, fm0);
-              }
-            }
-          }
-        }
-        int w0 = 0, h0 = 0, img = 0;
-        if (p.im2col == 1) {
-          const int pq = p.P * p.Q;
-          img = m0 / pq;
-          const int rem = m0 - img * pq;
-          const int pp = rem / p.Q, qq = rem - pp * p.Q;
-          w0 = qq * p.stride - p.pad;
-          h0 = pp * p.stride - p.pad;
-        } else if (p.im2col == 2) {
-          img = m_tile / p.P;
-          h0 = (m_tile - img * p.P) * p.stride;
-        }
-        if (has_res) {
-          const int rb = it & 1;
-          mbar_wait(res_empty_bar(rb), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 4);
-          mbar_arrive_expect_tx(res_full_bar(rb), (uint32_t)(SM::NBOX * SM::BOX_BYTES));
-#pragma unroll
-          for (int b = 0; b < SM::NBOX; ++b)
-            tma_load_2d(res_box(rb, b), &tmRes, res_full_bar(rb), p.res_coff + n0 + 64 * b, m0);
-        }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
-          const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + SM::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + (BRES ? 0 : SM::B_BYTES)));
-          const int tap = kb / p.cblocks;
-          const int c0 = (kb - tap * p.cblocks) * TC_BLOCK_K + p.in_coff;
-          if (p.im2col == 1) {
-            const int r = tap / p.S, s = tap - r * p.S;
-            tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
-          } else if (p.im2col == 2) {
-            tma_load_4d(a_dst, &tmA, full_bar(stage), 0, 0, h0 + kb, img);
-          } else {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), c0, m0);
-          }
-          if (!BRES) tma_load_2d(b_dst, &tmB, full_bar(stage), kb * TC_BLOCK_K, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16<BLOCK_N>();
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      if (BRES) mbar_wait(bres_full_bar, 0, p.err_flag, 7);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int ab = it & 1;
-        mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.err_flag, 2);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
-          const uint32_t b_addr = BRES ? smem_base + SM::BRES_OFFSET + kb * SM::B_BYTES : a_addr + SM::A_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(a_addr);
-          const uint64_t bdesc = make_smem_desc_sw128(b_addr);
-#pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma_commit(empty_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(tmem_full_bar(ab));
-      }
-    }
-  } else {
-    // ===== epilogue: warpgroup wg (warps 2+4wg .. 5+4wg) drains the tiles whose accumulator is TMEM buffer wg =====
-    const int wg = (warp - 2) >> 2;
-    const int quarter = warp & 3;
-    const int lrow = quarter * 32 + lane;
-    const uint32_t row_off = (uint32_t)lrow * 128u;
-    const uint32_t sw = (uint32_t)(lrow & 7);
-    const bool leader = (warp == 2 + 4 * wg && lane == 0);
-    for (int tile = blockIdx.x + wg * (int)gridDim.x, it = wg; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
-      const int m0 = m_tile * p.tile_rows;
-      const int n0 = n_tile * BLOCK_N;
-      const int ab = it & 1;
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      mbar_wait(tmem_full_bar(ab), ph, p.err_flag, 3);
-      tc_fence_after();
-      if (has_res) mbar_wait(res_full_bar(ab), ph, p.err_flag, 6);
-#pragma unroll 1
-      for (int b = 0; b < SM::NBOX; ++b) {
-        if (leader) bulk_wait_read<0>();   // this warpgroup's previous store has finished reading its staging box
-        epi_bar_sync(wg);
-        const uint32_t obase = out_box(wg) + row_off;
-        const uint32_t rbase = res_box(ab, b) + row_off;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BLOCK_N + b * 64 + half * 32), v);
-          tmem_ld_wait();
-          if (b == SM::NBOX - 1 && half == 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
-          }
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          const int col0 = n0 + b * 64 + half * 32;
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-            }
-          }
-          if (has_res) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 raw = lds_v4(rbase + ((((uint32_t)(half * 4 + c)) ^ sw) << 4));
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 r2 = __bfloat1622float2(h2[t]);
-                f[c * 8 + 2 * t] += r2.x;
-                f[c * 8 + 2 * t + 1] += r2.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 o;
-            __nv_bfloat162 h;
-            h = __floats2bfloat162_rn(f[c * 8 + 0], f[c * 8 + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
-            sts_v4(obase + ((((uint32_t)(half * 4 + c)) ^ sw) << 4), o);
-          }
-        }
-        if (has_res && b == SM::NBOX - 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(res_empty_bar(ab));
-        }
-        fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        epi_bar_sync(wg);
-        if (leader) {
-          tma_store_2d(&tmOut, out_box(wg), p.out_coff + n0 + b * 64, m0);
-          bulk_commit();
-        }
-      }
-    }
-    if (leader) bulk_wait_read<0>();
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
 // =====================================================================================================
-// v3: CTA-pair kernel (tcgen05 cta_group::2).  Two CTAs of a (2,1,1) cluster sit on the two SMs of a TPC and
+// CTA-pair kernel (tcgen05 cta_group::2).  Two CTAs of a (2,1,1) cluster sit on the two SMs of a TPC and
 // compute one 256 x BLOCK_N output tile together: each CTA loads its own 128 activation rows and HALF of the
 // weight tile (BLOCK_N/2 rows); the leader CTA issues one M=256 MMA per K step that reads A and B from both
 // CTAs' shared memory and writes rows 0..127 of the accumulator into its own TMEM and rows 128..255 into the
-// peer's.  Per output element this halves the weight traffic L2 -> SM, which is what bounded v2
+// peer's.  Per output element this halves the weight traffic L2 -> SM, which is what bounded the one-CTA persistent kernel
 // (profiles/README.md: 694 MB of smem fill per 3x3 256->256 launch = 11.7 TB/s, the measured L2 ceiling).
 //   * smem ring per CTA: STAGES x (16 KB A + BLOCK_N/2 x 128 B of B); both CTAs' TMA loads complete on the
 //     LEADER's full barrier, one tcgen05.commit.multicast frees the slot in both CTAs;
@@ -977,7 +653,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t lbar0 = mapa_shared(full_bar(0), 0);   // leader CTA's full barriers
     const uint32_t tx_bytes = (uint32_t)(2 * (p.a_bytes + (BRES ? 0 : SM::BH_BYTES)));
     const int b_row0 = (int)rank * (BLOCK_N / 2);
-    const int krot0 = (int)(((long long)pair * p.k_rot) % p.num_k_blocks);
     // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
     // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
     // busy epilogue never stalls the operand ring
@@ -1020,7 +695,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
       const int n_tile = tile % p.n_tiles;
       const int mp = tile / p.n_tiles;
-      const int m_tile = (p.m_rev ? m_pairs - 1 - mp : mp) * 2 + (int)rank;
+      const int m_tile = mp * 2 + (int)rank;
       const int m0 = m_tile * p.tile_rows;
       const int n0 = n_tile * BLOCK_N;
       int w0 = 0, h0 = 0, img = 0;
@@ -1035,10 +710,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         img = m_tile / p.P;
         h0 = (m_tile - img * p.P) * p.stride;
       }
-      // Every CTA pair walks K from a different starting block: the pairs run in lock step, and with a common order all
-      // 74 of them ask L2 for the same weight lines at the same moment.  fp32 accumulation order differs per pair only.
-      int kb = krot0;
-      int cb = kb % p.cblocks, tap_s = (kb / p.cblocks) % p.S, tap_r = (kb / p.cblocks) / p.S;   // k-block -> (filter row, column, 64-channel block)
+      int kb = 0, cb = 0, tap_s = 0, tap_r = 0;   // k-block -> (filter row, column, 64-channel block)
       for (int kk = 0; kk < p.num_k_blocks; ++kk) {
         if (HAS_RES) issue_pending(false);
         TC3_TIMED(0, mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1));
@@ -1062,8 +734,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        if (++kb == p.num_k_blocks) { kb = 0; cb = 0; tap_s = 0; tap_r = 0; }
-        else if (++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
+        ++kb;
+        if (++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
       }
       if (HAS_RES) {
         issue_pending(true);   // the tile before this one: its boxes were freed at least one whole tile ago
@@ -1087,7 +759,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const int krot0 = (int)(((long long)pair * p.k_rot) % p.num_k_blocks);
       if (dbg_on) t_loop0 = clock64();
       if (BRES) mbar_wait(bres_full_bar, 0, p.err_flag, 7);
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
@@ -1095,8 +766,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         TC3_TIMED(1, mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
-        int kb = krot0;
         for (int kk = 0; kk < p.num_k_blocks; ++kk) {
+          const int kb = kk;
           TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
           tc_fence_after();
           if (elect_one()) {
@@ -1122,7 +793,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (++kb == p.num_k_blocks) kb = 0;
         }
       }
       if (dbg_on && lane == 0) {
@@ -1156,43 +826,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // one tile ahead into a register, parked in smem and read back as broadcast LDS.128.
     float bias_pre = 0.f;
     if (has_bias && wt < SM::CW && tile < total_tiles) bias_pre = __ldg(p.bias + (tile % p.n_tiles) * BLOCK_N + colbase + wt);
-    // L2 prefetch of a future tile's DRAM-resident operands (see TcKernelParams::pf_a)
-    auto prefetch_tile = [&](int ft) {
-      if (ft >= total_tiles) return;
-      const int fn = ft % p.n_tiles;
-      const int fmp = ft / p.n_tiles;
-      const int fm0 = ((p.m_rev ? m_pairs - 1 - fmp : fmp) * 2 + (int)rank) * TC_BLOCK_M;
-      if (p.pf_a != nullptr) {
-        // the n-tiles that share these activation rows run on other CTA pairs at the same time: split the rows
-        const int rows_per = p.n_tiles <= TC_BLOCK_M ? TC_BLOCK_M / p.n_tiles : 1;
-        const int r0 = fn * rows_per;
-        const int nlines = (fn < TC_BLOCK_M ? rows_per : 0) * p.pf_a_lines;
-        for (int l = wt + (SM::SPLIT_COLS ? g * 128 : 0); l < nlines; l += (SM::SPLIT_COLS ? 256 : 128)) {
-          const int row = fm0 + r0 + l / p.pf_a_lines;
-          if (row < p.M)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_a + (long long)row * p.pf_a_pitch + (l % p.pf_a_lines) * 128));
-        }
-      }
-      if (HAS_RES && p.pf_res_pitch != 0) {
-        constexpr int RL = BLOCK_N * 2 / 128;   // lines per residual row of this tile
-        const char* rbase = reinterpret_cast<const char*>(p.res) + (size_t)(p.res_coff + fn * BLOCK_N) * 2;
-        for (int l = wt + (SM::SPLIT_COLS ? g * 128 : 0); l < TC_BLOCK_M * RL; l += (SM::SPLIT_COLS ? 256 : 128)) {
-          const int row = fm0 + l / RL;
-          if (row < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase + (long long)row * p.pf_res_pitch + (l % RL) * 128));
-        }
-      }
-    };
-    const bool pf_on = p.pf_a != nullptr || (HAS_RES && p.pf_res_pitch != 0);
-    if (pf_on) prefetch_tile(tile + step);
     if (dbg_on) t_loop0 = clock64();
     for (; tile < total_tiles; tile += step, it += (SM::SPLIT_COLS ? 1 : 2), ++lt) {
       const int n_tile = tile % p.n_tiles;
       const int mp = tile / p.n_tiles;
-      const int m_tile = (p.m_rev ? m_pairs - 1 - mp : mp) * 2 + (int)rank;
+      const int m_tile = mp * 2 + (int)rank;
       const int m0 = m_tile * p.tile_rows;
       const int n0 = n_tile * BLOCK_N;
       const int ab = it & 1;
-      if (pf_on) prefetch_tile(tile + 2 * step);
       TC3_TIMED(0, mbar_wait(tmem_full_bar(ab), (uint32_t)((it >> 1) & 1), p.err_flag, 3));
       tc_fence_after();
       const uint32_t bias_s = bias_wg + (uint32_t)((lt & 1) * SM::CW * 4);
@@ -1725,10 +1366,9 @@ static int load_driver_fns() {
 
 struct TcConvPlan {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  CUtensorMap tmBh;   // v3: weight map with a BLOCK_N/2-row box (each CTA of the pair loads half of the tile)
-  CUtensorMap tmOut32, tmOutTail;   // v3: per-warp 32-row output boxes (+ the short last box of a 112-row stem tile)
-  int v2;
-  int v3;
+  CUtensorMap tmBh;   // pair kernel: weight map with a BLOCK_N/2-row box (each CTA of the pair loads half of the tile)
+  CUtensorMap tmOut32, tmOutTail;   // pair kernel: per-warp 32-row output boxes (+ the short last box of a 112-row stem tile)
+  int v3;             // 1: the CTA-pair kernel serves this layer; 0: the one-CTA kernel (Cout = 32, NIB_TC_V1)
   int block_n, stages;
   int im2col;
   int tile_rows;
@@ -1772,9 +1412,8 @@ bool tc_conv_is_stem(const ConvParams& p) {
 // padded to 128 B rows by the copy engine, measured with tools/stem_diag.py, hence SWIZZLE_64B + matching UMMA
 // descriptors).  K = 4 x 64 instead of 7 x 64: 43 % fewer activation bytes through the TMA and 43 % fewer MMAs.
 // CTA-pair kernel with resident weights only.
-static int tc_version();
 bool tc_conv_is_stem4(const ConvParams& p) {
-  return tc_version() >= 3 && p.R == 7 && p.S == 7 && p.stride == 2 && p.pad == 3 && p.Cin <= 4 && p.in_cstride == 4 &&
+  return p.R == 7 && p.S == 7 && p.stride == 2 && p.pad == 3 && p.Cin <= 4 && p.in_cstride == 4 &&
          p.in_coff == 0 && p.in_halo == 3 && p.Cout % 64 == 0 && p.Q <= TC_BLOCK_M && p.out_halo == 0 &&
          p.out_cstride % 8 == 0 && p.out_coff % 8 == 0 && p.pre_scale == nullptr && p.res == nullptr &&
          p.w_alt != nullptr && (p.Win + 2 * p.in_halo) % 2 == 0 && (p.Win + 2 * p.in_halo) >= 2 * (p.Q - 1) + 8 &&
@@ -1795,44 +1434,20 @@ bool tc_conv_supported(const ConvParams& p) {
   return true;
 }
 
-static int tc_version();
-static int pick_block_n(int Cout, bool has_res = true, int ksize = 1) {
-  const char* e = getenv("NIB_TC_BLOCK_N");
-  if (e) {
-    int v = atoi(e);
-    if ((v == 32 || v == 64 || v == 128 || v == 256) && Cout % v == 0) return v;
-  }
-  // tuning knobs for the sweep: block-N of residual-free 3x3 / 1x1 layers
-  const char* e3 = getenv(ksize > 1 ? "NIB_TC_BLOCK_N_3X3" : "NIB_TC_BLOCK_N_1X1");
-  if (e3 && !has_res) {
-    int v = atoi(e3);
-    if ((v == 64 || v == 128 || v == 256) && Cout % v == 0) return v;
-  }
-  if ((!has_res || tc_version() >= 3) && Cout % 256 == 0) return 256;   // 128x256 tiles per CTA: L2 -> SM fill is the limiter
+// Widest tile the layer allows: 128 x 256 per CTA (256 x 256 per pair) - L2 -> SM fill is the limiter, and the pair
+// kernel halves the weight bytes per output element.  Cout = 32 (DenseNet growth) stays on the one-CTA kernel.
+static int pick_block_n(int Cout) {
+  if (Cout % 256 == 0) return 256;
   if (Cout % 128 == 0) return 128;
   if (Cout % 64 == 0) return 64;
   return 32;
 }
 
-// v2 (persistent, TMA-store epilogue) needs 64-column output boxes: BLOCK_N in {64,128}, Cout % BLOCK_N == 0.
-static int tc_version() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("NIB_TC_VER");
-    v = e ? atoi(e) : 3;
-    if (v < 1 || v > 3) v = 3;
-    const char* e1 = getenv("NIB_TC_V1");
-    if (e1 && atoi(e1) != 0) v = 1;
-  }
-  return v;
-}
-
 static int finish_plan(TcConvPlan* plan, const ConvParams& p, int max_batch, const void* w_ptr, int K) {
-  plan->v2 = 0;
   plan->v3 = 0;
-  if (tc_version() == 1) return NIB_OK;
-  const bool bn_ok = plan->block_n == 64 || plan->block_n == 128 ||
-                     (plan->block_n == 256 && (p.res == nullptr || tc_version() >= 3));
+  static const bool v1_only = getenv("NIB_TC_V1") != nullptr;   // debugging aid: everything on the one-CTA kernel
+  if (v1_only) return NIB_OK;
+  const bool bn_ok = plan->block_n == 64 || plan->block_n == 128 || plan->block_n == 256;
   if (!bn_ok || p.Cout % plan->block_n != 0) return NIB_OK;
   const uint64_t rows = (uint64_t)max_batch * p.P * p.Q;
   int rc = encode_2d_bf16(&plan->tmOut, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
@@ -1844,19 +1459,16 @@ static int finish_plan(TcConvPlan* plan, const ConvParams& p, int max_batch, con
   } else {
     plan->tmRes = plan->tmOut;
   }
-  plan->v2 = 1;
-  if (tc_version() >= 3) {
-    rc = encode_2d_bf16(&plan->tmBh, w_ptr, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, TC_BLOCK_K,
-                        (uint32_t)(plan->block_n / 2));
-    if (rc != NIB_OK) return rc;
-    rc = encode_2d_bf16(&plan->tmOut32, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64, 32);
-    if (rc != NIB_OK) return rc;
-    const int tail = plan->tile_rows % 32;
-    rc = encode_2d_bf16(&plan->tmOutTail, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
-                        (uint32_t)(tail ? tail : 32));
-    if (rc != NIB_OK) return rc;
-    plan->v3 = 1;
-  }
+  rc = encode_2d_bf16(&plan->tmBh, w_ptr, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, TC_BLOCK_K,
+                      (uint32_t)(plan->block_n / 2));
+  if (rc != NIB_OK) return rc;
+  rc = encode_2d_bf16(&plan->tmOut32, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64, 32);
+  if (rc != NIB_OK) return rc;
+  const int tail = plan->tile_rows % 32;
+  rc = encode_2d_bf16(&plan->tmOutTail, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
+                      (uint32_t)(tail ? tail : 32));
+  if (rc != NIB_OK) return rc;
+  plan->v3 = 1;
   return NIB_OK;
 }
 
@@ -1870,7 +1482,7 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
   TcConvPlan* plan = new TcConvPlan();
   memset(plan, 0, sizeof(*plan));
   plan->err_flag = g_err_flag;
-  plan->block_n = pick_block_n(p.Cout, p.res != nullptr, p.R);
+  plan->block_n = pick_block_n(p.Cout);
   plan->tile_rows = TC_BLOCK_M;
   if (tc_conv_is_stem4(p)) {
     plan->im2col = 3;
@@ -1999,7 +1611,8 @@ static bool compact_1x1(const ConvParams& p) {
 bool tc_fuse_supported(const ConvParams& c, const ConvParams& a) {
   const char* e = getenv("NIB_TC_FUSE");
   if (e != nullptr && atoi(e) == 0) return false;
-  if (tc_version() < 3) return false;
+  static const bool v1_only = getenv("NIB_TC_V1") != nullptr;
+  if (v1_only) return false;
   if (!compact_1x1(c) || !compact_1x1(a)) return false;
   if (c.res == nullptr || c.res_C != c.Cout || c.res_cstride != c.Cout || c.res_coff != 0) return false;
   if (c.Cin % TC_BLOCK_K != 0 || c.Cin > 256 || c.Cout % 256 != 0 || c.Cout > 1024) return false;
@@ -2143,23 +1756,6 @@ static int launch_tc(const TcConvPlan* plan, const TcKernelParams& kp, int tiles
 }
 
 template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
-static int launch_tc2(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
-  using SM = Tc2Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
-  static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NIB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES, BRES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr_set = true;
-  }
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_tc2_kernel<BLOCK_N, STAGES, HAS_RES, BRES><<<grid, TC2_THREADS, SM::TOTAL, st>>>(plan->tmA, plan->tmB, plan->tmOut,
-                                                                                         plan->tmRes, kp);
-  NIB_LAUNCH_CHECK();
-  return NIB_OK;
-}
-
-template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
 static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStream_t st) {
   using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
   static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -2170,8 +1766,7 @@ static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStre
     attr_set = true;
   }
   const int pair_tiles = ((kp.m_tiles + 1) / 2) * kp.n_tiles;
-  static const int pair_cap = [] { const char* e = getenv("NIB_TC_PAIRS"); return e ? atoi(e) : 0; }();   // experiment: leave SMs to a second stream
-  const int max_pairs = pair_cap > 0 && pair_cap < num_sms() / 2 ? pair_cap : num_sms() / 2;
+  const int max_pairs = num_sms() / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
   // launched with programmatic stream serialization: the CTAs become resident (and run their prologue) as the SMs of
   // the previous kernel free up, then block in griddepcontrol.wait until that kernel has completed
@@ -2200,21 +1795,9 @@ static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int til
     const bool res = kp.res != nullptr;
     if (plan->block_n == 256) return res ? launch_tc3<256, 5, true>(plan, kp, st) : launch_tc3<256, 6, false>(plan, kp, st);
     if (plan->block_n == 128) return res ? launch_tc3<128, 6, true>(plan, kp, st) : launch_tc3<128, 8, false>(plan, kp, st);
-    static const bool no_bres = getenv("NIB_TC_NO_BRES") != nullptr;
-    if (plan->block_n == 64 && !res && kp.n_tiles == 1 && kp.num_k_blocks <= TC3_BRES_KBLOCKS && !no_bres)
+    if (plan->block_n == 64 && !res && kp.n_tiles == 1 && kp.num_k_blocks <= TC3_BRES_KBLOCKS)
       return launch_tc3<64, 9, false, true>(plan, kp, st);   // resident weights: stem, 56x56 64-channel layers
     if (plan->block_n == 64) return res ? launch_tc3<64, 9, true>(plan, kp, st) : launch_tc3<64, 9, false>(plan, kp, st);
-  }
-  if (plan->v2 && !kp.out_f32) {
-    // stage depth is what hides the L2 -> smem latency (Little's law: ~1.5 us x per-SM fill rate); the residual
-    // double buffer costs 2 x BLOCK_N/64 x 16 KB, so layers without a residual get the deeper ring.
-    const bool res = kp.res != nullptr;
-    static const bool no_bres = getenv("NIB_TC_NO_BRES") != nullptr;
-    if (plan->block_n == 64 && !res && kp.n_tiles == 1 && kp.num_k_blocks <= TC2_BRES_KBLOCKS && !no_bres)
-      return launch_tc2<64, 6, false, true>(plan, kp, tiles, st);   // resident weights: stem, 56x56 64-channel layers
-    if (plan->block_n == 64) return res ? launch_tc2<64, 5, true>(plan, kp, tiles, st) : launch_tc2<64, 7, false>(plan, kp, tiles, st);
-    if (plan->block_n == 128) return res ? launch_tc2<128, 3, true>(plan, kp, tiles, st) : launch_tc2<128, 5, false>(plan, kp, tiles, st);
-    if (plan->block_n == 256 && !res) return launch_tc2<256, 4, false>(plan, kp, tiles, st);
   }
   switch (plan->block_n) {
     case 32:  return launch_tc<32, 4>(plan, kp, tiles, st);
@@ -2307,33 +1890,6 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.tile_rows = plan->tile_rows;
   kp.a_bytes = plan->tile_rows * TC_BLOCK_K * 2;
   kp.m_tiles = ceil_div(p.M, plan->tile_rows);
-  {
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("NIB_TC_PF"); pf = e ? atoi(e) : 0; }   // measured: no gain on B200 (profiles/README.md), off by default
-    kp.pf_dist = pf;
-  }
-  {
-    static int krot = -1;
-    if (krot < 0) { const char* e = getenv("NIB_TC_KROT"); krot = e ? atoi(e) : 0; }   // measured: no gain from de-synchronising the pairs; default keeps one K order
-    kp.k_rot = krot;
-  }
-  {
-    // serpentine M order: the 1x1 reductions (Cin > Cout) read the tensor the previous expansion just wrote, and the
-    // expansion's residual is the tensor the reduction just read; walking the reductions backwards makes each layer start
-    // on the rows its predecessor touched last
-    static int serp = -1;
-    if (serp < 0) { const char* e = getenv("NIB_TC_SERP"); serp = e ? atoi(e) : 0; }
-    kp.m_rev = (serp && plan->v3 && p.R == 1 && p.stride == 1 && p.Cin > p.Cout) ? 1 : 0;
-  }
-  static const bool no_pf = getenv("NIB_TC_L2PF") == nullptr;   // measured: no gain (profiles/README.md); opt-in
-  if (plan->v3 && !no_pf && plan->tile_rows == TC_BLOCK_M) {
-    if (plan->im2col == 0 && (p.Cin * 2) % 128 == 0) {
-      kp.pf_a = reinterpret_cast<const char*>(p.in) + (size_t)p.in_coff * 2;
-      kp.pf_a_pitch = (long long)p.in_cstride * 2;
-      kp.pf_a_lines = p.Cin * 2 / 128;
-    }
-    kp.pf_res_pitch = (long long)p.res_cstride * 2;
-  }
   const int tiles = kp.m_tiles * kp.n_tiles;
   static const bool dbg = getenv("NIB_TC_DBG") != nullptr;
   if (dbg && plan->v3) return tc_launch_debug(plan, kp, p, tiles, st);
