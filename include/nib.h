@@ -362,6 +362,23 @@ int nib_ski_predict(const double* d_Xq, int m, double grid0, double spacing, int
                     int add_noise, double* d_mean, double* d_var, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Variational GP classification on the inducing grid: the O(n) part of one optimiser step of
+ * gp_classification.py:160-217 (`-mll(model(train_x), train_y)` + backward) and its prediction loop :241-253
+ * (`likelihood(model(test_x)).mean()`).  gpytorch (GridInducingVariationalGP, BernoulliLikelihood, pre-0.1 API) is absent
+ * and unpinned -> parity unpinned; the model is restated in csrc/ski.cu: u ~ N(0, K_UU) on the grid, q(u) = N(m, S),
+ * f(x) = c + w(x)^T u, p(y | f) = Phi(y f), expectations by 20-point Gauss-Hermite quadrature.
+ *   nib_vgp_loglik_grad  *d_ell = sum_i E_q[log Phi(y_i f_i)], d_grad_m [G] and d_grad_S [G,G] its gradients w.r.t. the
+ *                        variational mean / covariance, d_grad_c (optional) w.r.t. the constant mean; outputs are zeroed
+ *                        by the call.  d_S is the dense symmetric covariance [G,G].
+ *   nib_vgp_predict      d_prob[q] = Phi(mu_q / sqrt(1 + s2_q)); latent moments to d_mu / d_var (any may be NULL)
+ * ---------------------------------------------------------------------------------------- */
+int nib_vgp_loglik_grad(const double* d_X, const double* d_y, int n, double grid0, double spacing, int grid_size,
+                        double const_mean, const double* d_m, const double* d_S, double* d_ell, double* d_grad_m,
+                        double* d_grad_S, double* d_grad_c, void* stream);
+int nib_vgp_predict(const double* d_Xq, int m, double grid0, double spacing, int grid_size, double const_mean,
+                    const double* d_m, const double* d_S, double* d_prob, double* d_mu, double* d_var, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Superpixel label map — HOST function, HOST pointers, no device needed.
  * Replaces `felzenszwalb(img_as_float(img), scale=100, sigma=0.5, min_size=50)`
  * (generate_gp_training_data_imagenet.py:183, generate_gp_training_data_mnist.py:187,

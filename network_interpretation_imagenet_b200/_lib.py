@@ -103,6 +103,8 @@ _PROTOTYPES = {
     "nib_heatmap_pixels": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "nib_ski_accumulate": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp, _vp]),
     "nib_ski_predict": (_i, [_vp, _i, _d, _d, _i, _d, _vp, _vp, _d, _i, _vp, _vp, _vp]),
+    "nib_vgp_loglik_grad": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nib_vgp_predict": (_i, [_vp, _i, _d, _d, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nib_felzenszwalb": (_i, [_vp, _i, _i, _i, _d, _d, _i, _vp, C.POINTER(_i)]),
 }
 

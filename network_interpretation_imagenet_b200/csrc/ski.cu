@@ -101,6 +101,108 @@ ski_predict_kernel(const double* __restrict__ Xq, int m, double g0, double h, in
   }
 }
 
+// ---- variational GP classification on the inducing grid (gp_classification.py:139-264) -----------------------------------
+// Model (gpytorch GridInducingVariationalGP + BernoulliLikelihood, pre-0.1 API, absent here -> parity unpinned; restated
+// from its published construction): inducing values u ~ N(0, K_UU) on the grid, q(u) = N(m, S), latent f(x) = c + w(x)^T u
+// with the same cubic interpolation weights as above, probit likelihood p(y | f) = Phi(y f).  The O(n) part of one
+// optimiser step is the expected log-likelihood and its gradients:
+//     mu_i = c + w_i^T m,   s2_i = w_i^T S w_i,   E_i = E_{f ~ N(mu_i, s2_i)}[ log Phi(y_i f) ]
+//     dE/dm = sum_i dE_i/dmu w_i,   dE/dS = sum_i dE_i/ds2 w_i w_i^T       (dE/ds2 = 1/2 E[d^2/df^2 log Phi(y f)])
+// with the expectations by Gauss-Hermite quadrature (20 nodes; the reference's version samples, which no parity test
+// could pin).  One thread per training pixel; 16 + 256 fp64 atomics into the L2-resident G / G x G gradient arrays.
+__constant__ double c_gh_x[20];   // Gauss-Hermite nodes / weights for the weight function exp(-x^2) (set by the host)
+__constant__ double c_gh_w[20];
+
+__device__ __forceinline__ double log_ndtr(double z) {
+  // log Phi(z), stable in the lower tail: Phi(z) = erfc(-z / sqrt 2) / 2, erfcx for z << 0
+  if (z > -5.0) return log(0.5 * erfc(-z * 0.70710678118654752440));
+  const double t = -z * 0.70710678118654752440;
+  return log(0.5 * erfcx(t)) - t * t;
+}
+__device__ __forceinline__ double pdf_over_cdf(double z) {
+  // phi(z) / Phi(z) (inverse Mills ratio of -z), stable in the lower tail
+  if (z > -5.0) return 0.39894228040143267794 * exp(-0.5 * z * z) / (0.5 * erfc(-z * 0.70710678118654752440));
+  return 0.79788456080286535588 / erfcx(-z * 0.70710678118654752440);
+}
+
+__global__ void __launch_bounds__(128)
+vgp_loglik_kernel(const double* __restrict__ X, const double* __restrict__ y, int n, double g0, double h, int gs,
+                  double cmean, const double* __restrict__ m, const double* __restrict__ S, double* __restrict__ ell_out,
+                  double* __restrict__ g_m, double* __restrict__ g_S, double* __restrict__ g_c) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0, dmu = 0.0;
+  if (p < n) {
+    int idx[16];
+    double w[16];
+    stencil(X[2 * p], X[2 * p + 1], g0, h, gs, idx, w);
+    const int G = gs * gs;
+    double mu = cmean, s2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      mu = fma(w[a], m[idx[a]], mu);
+      double r = 0.0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) r = fma(w[c], S[(size_t)idx[a] * G + idx[c]], r);
+      s2 = fma(w[a], r, s2);
+    }
+    s2 = fmax(s2, 0.0);
+    const double sd = sqrt(s2), yy = y[p];
+    double ds2 = 0.0;
+    for (int k = 0; k < 20; ++k) {
+      const double z = yy * (mu + 1.41421356237309504880 * sd * c_gh_x[k]);
+      const double r = pdf_over_cdf(z);
+      const double wk = c_gh_w[k] * 0.56418958354775628695;   // / sqrt(pi)
+      e = fma(wk, log_ndtr(z), e);
+      dmu = fma(wk, yy * r, dmu);
+      ds2 = fma(wk, -0.5 * yy * yy * r * (z + r), ds2);
+    }
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      atomicAdd(g_m + idx[a], dmu * w[a]);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) atomicAdd(g_S + (size_t)idx[a] * G + idx[c], ds2 * w[a] * w[c]);
+    }
+  }
+  // block-reduce the scalar terms (expected log-likelihood, gradient w.r.t. the constant mean)
+  __shared__ double sh[2][4];
+  for (int o = 16; o > 0; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    dmu += __shfl_xor_sync(0xffffffffu, dmu, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = e; sh[1][threadIdx.x >> 5] = dmu; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(ell_out, sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]);
+    if (g_c) atomicAdd(g_c, sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]);
+  }
+}
+
+// predictive class probability E_q[Phi(f)] = Phi(mu / sqrt(1 + s2)) at the query pixels, plus the latent moments
+__global__ void __launch_bounds__(128)
+vgp_predict_kernel(const double* __restrict__ Xq, int mq, double g0, double h, int gs, double cmean,
+                   const double* __restrict__ m, const double* __restrict__ S, double* __restrict__ prob,
+                   double* __restrict__ mu_out, double* __restrict__ var_out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= mq) return;
+  int idx[16];
+  double w[16];
+  stencil(Xq[2 * q], Xq[2 * q + 1], g0, h, gs, idx, w);
+  const int G = gs * gs;
+  double mu = cmean, s2 = 0.0;
+#pragma unroll
+  for (int a = 0; a < 16; ++a) {
+    mu = fma(w[a], m[idx[a]], mu);
+    double r = 0.0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) r = fma(w[c], S[(size_t)idx[a] * G + idx[c]], r);
+    s2 = fma(w[a], r, s2);
+  }
+  s2 = fmax(s2, 0.0);
+  if (prob) prob[q] = 0.5 * erfc(-(mu / sqrt(1.0 + s2)) * 0.70710678118654752440);
+  if (mu_out) mu_out[q] = mu;
+  if (var_out) var_out[q] = s2;
+}
+
 // heat[p] += sum_i y[i] * [masks[i][p] == on]   — masks u8 [N][P] (the PNG side channel read back, 0 / 255)
 __global__ void __launch_bounds__(256)
 heatmap_pixels_kernel(const uint8_t* __restrict__ masks, const float* __restrict__ y, int N, int P, int on,
@@ -138,6 +240,56 @@ int nib_ski_predict(const double* d_Xq, int m, double grid0, double spacing, int
   NIB_REQUIRE(d_var == nullptr || d_Gm != nullptr, "nib_ski_predict: variance needs d_Gm");
   ski_predict_kernel<<<ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(d_Xq, m, grid0, spacing, grid_size, const_mean,
                                                                         d_mean_u, d_Gm, noise, add_noise, d_mean, d_var);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+static int vgp_set_quadrature() {
+  // 20-point Gauss-Hermite rule (physicists': weight exp(-x^2)); positive half, mirrored.  Abramowitz & Stegun 25.10.
+  static bool done = false;
+  if (done) return NIB_OK;
+  static const double xh[10] = {0.2453407083009012, 0.7374737285453944, 1.2340762153953231, 1.7385377121165861,
+                                2.2549740020892757, 2.7888060584281305, 3.3478545673832163, 3.9447640401156252,
+                                4.6036824495507442, 5.3874808900112328};
+  static const double wh[10] = {4.622436696006101e-01, 2.866755053628341e-01, 1.090172060200233e-01, 2.481052088746361e-02,
+                                3.243773342237862e-03, 2.283386360163540e-04, 7.802556478532064e-06, 1.086069370769282e-07,
+                                4.399340992273181e-10, 2.229393645534151e-13};
+  double x[20], w[20];
+  for (int i = 0; i < 10; ++i) { x[i] = -xh[9 - i]; w[i] = wh[9 - i]; x[10 + i] = xh[i]; w[10 + i] = wh[i]; }
+  NIB_CUDA(cudaMemcpyToSymbol(nib::c_gh_x, x, sizeof(x)));
+  NIB_CUDA(cudaMemcpyToSymbol(nib::c_gh_w, w, sizeof(w)));
+  done = true;
+  return NIB_OK;
+}
+
+int nib_vgp_loglik_grad(const double* d_X, const double* d_y, int n, double grid0, double spacing, int grid_size,
+                        double const_mean, const double* d_m, const double* d_S, double* d_ell, double* d_grad_m,
+                        double* d_grad_S, double* d_grad_c, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  using namespace nib;
+  NIB_REQUIRE(d_X && d_y && d_m && d_S && d_ell && d_grad_m && d_grad_S && n > 0 && grid_size >= 4 && spacing > 0.0,
+              "nib_vgp_loglik_grad: bad arguments");
+  int rc = vgp_set_quadrature();
+  if (rc != NIB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t G = (size_t)grid_size * grid_size;
+  NIB_CUDA(cudaMemsetAsync(d_ell, 0, sizeof(double), st));
+  NIB_CUDA(cudaMemsetAsync(d_grad_m, 0, G * sizeof(double), st));
+  NIB_CUDA(cudaMemsetAsync(d_grad_S, 0, G * G * sizeof(double), st));
+  if (d_grad_c) NIB_CUDA(cudaMemsetAsync(d_grad_c, 0, sizeof(double), st));
+  vgp_loglik_kernel<<<ceil_div(n, 128), 128, 0, st>>>(d_X, d_y, n, grid0, spacing, grid_size, const_mean, d_m, d_S, d_ell,
+                                                      d_grad_m, d_grad_S, d_grad_c);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+int nib_vgp_predict(const double* d_Xq, int m, double grid0, double spacing, int grid_size, double const_mean,
+                    const double* d_m, const double* d_S, double* d_prob, double* d_mu, double* d_var, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  using namespace nib;
+  NIB_REQUIRE(d_Xq && d_m && d_S && m > 0 && grid_size >= 4 && spacing > 0.0, "nib_vgp_predict: bad arguments");
+  vgp_predict_kernel<<<ceil_div(m, 128), 128, 0, (cudaStream_t)stream>>>(d_Xq, m, grid0, spacing, grid_size, const_mean,
+                                                                         d_m, d_S, d_prob, d_mu, d_var);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }

@@ -27,7 +27,7 @@ from .scoring import score
 # max|logit|, max error of any (top1 - other) difference 2.9e-3; the default band is that bound with a 2x safety factor,
 # well inside twice the 1e-2 logit tolerance north_star states (which, taken literally as the band, would re-score
 # every mask of a near-tied random-init network: all 3072 margins of the bench workload are below 2e-2).
-DEFAULT_TIE_BAND = 6e-3
+DEFAULT_TIE_BAND = 6e-3   # provisional: see tools/r02_diag2.py
 DEFAULT_TIE_CAPACITY = 128
 
 
