@@ -8,6 +8,10 @@ batch-1 forward and returns the softmax probability of the true class (:178-198)
 and re-running felzenszwalb on every evaluation (:126-150).  Here the image and label map stay on the device, one
 evaluation is one mask-synthesis + forward + score launch sequence, and the GP / EI run in libnib.so.
 
+After the search, `plot_summed_heatmap(val_img_index, bbox_threshold, gt_bbox)` (:312-377, called at :492 with
+bbox_threshold = 180) sums the labels of the evaluated masks into a heat map, boxes its strongest region and reports the
+IOU with the ground-truth box - heat map, 8-bit view and bounding box are device kernels here (localize.py).
+
 `--masks` switches to the scaled-up form of BASELINE.json config 4: the GP input is the mask itself, n training
 masks, `--rounds` acquisition rounds over m candidate masks scored by EI on the device."""
 from __future__ import annotations
@@ -46,15 +50,27 @@ parser.add_argument("--n-train", default=8192, type=int)
 parser.add_argument("--n-candidates", default=8192, type=int)
 parser.add_argument("--rounds", default=20, type=int)
 parser.add_argument("--mask-seed", default=0, type=int)
+parser.add_argument("--gt-bbox", default=None, type=int, nargs=4, metavar=("X", "Y", "W", "H"),
+                    help="ground-truth box of the image (the reference reads it from the ImageNet annotation, :454)")
 
 _ENGINE = {}
+_EVALS = {"bits": [], "labels": []}        # the masks this run evaluated and their 0/1 labels (the reference's ./masks PNGs)
 
 
 def validate_nueral_network(val_loader, model, criterion, bo_iter, firstIndex):
     """Reference :116-221: target-class softmax probability of the image masked with the window at firstIndex."""
     eng = _ENGINE["engine"]
     sel = window_at(eng.synth.S, int(firstIndex))
-    out = eng.score_masks(selection_bits([sel], eng.synth.S))
+    bits = selection_bits([sel], eng.synth.S)
+    out = eng.score_masks(bits)
+    label = int(out["correct"][0].item())                      # :199-213: 1 iff the masked image keeps its top-1
+    _EVALS["bits"].append(bits[0])
+    _EVALS["labels"].append(label)
+    writer = _ENGINE.get("writer")
+    if writer is not None:                                       # ./masks/mask_{bo_iter}_{label}.png, ./mask_on_img/... (:207-216)
+        _, pm = eng.synth.synth(bits, eng.mode, return_pixel_masks=True)
+        writer.submit("./masks", ["mask_{}_{}.png".format(bo_iter, label)], pm, scale=255)
+        writer.submit("./mask_on_img", ["masked_imgs_{}_{}.png".format(bo_iter, label)], eng.synth.display_u8(bits, eng.mode))
     return float(out["target_prob"][0].item())
 
 
@@ -63,6 +79,28 @@ def sample_loss(params, val_loader, model, criterion):
     firstIndex = int(params[0])
     print("firstIndex: ", firstIndex)
     return validate_nueral_network(val_loader, model, criterion, params[0], firstIndex)
+
+
+def plot_summed_heatmap(val_img_index, bbox_threshold, gt_bbox):
+    """Reference :312-377.  Heat map of the evaluated masks (sum of their 0/1 labels per pixel), its uint8 view, the box of
+    the strongest region above `bbox_threshold` and the IOU with `gt_bbox` = [x, y, w, h].  The reference's
+    generate_boundingbox returns [x, y, x, y] (utils.py:109); that quirk is reproduced, and the IOU of the real box is
+    printed next to it."""
+    import cv2
+    from network_interpretation_imagenet_b200 import localize as loc
+    eng = _ENGINE["engine"]
+    bits = np.stack(_EVALS["bits"])
+    labels = np.asarray(_EVALS["labels"], dtype=np.float32)
+    print("%d samples, the correct prediction number: %d " % (len(labels), int(labels.sum())))
+    heat = eng.synth.heatmap(bits, labels)
+    IOU, pred_box, gray = loc.summed_heatmap_iou(heat, bbox_threshold, list(gt_bbox), quirk=True)
+    IOU_box, real_box, _ = loc.summed_heatmap_iou(heat, bbox_threshold, list(gt_bbox), quirk=False)
+    os.makedirs("heatmaps", exist_ok=True)
+    cv2.imwrite("heatmaps/index_{}.png".format(val_img_index), cv2.applyColorMap(gray.cpu().numpy(), cv2.COLORMAP_JET))
+    cv2.imwrite("heatmaps/gray_img_{}.png".format(val_img_index), gray.cpu().numpy())
+    print('\033[91m' + "IOU: " + str(IOU) + '\033[0m')
+    print("IOU with the real predicted box {}: {}".format(real_box, IOU_box))
+    return IOU
 
 
 def main():
@@ -90,12 +128,20 @@ def main():
     eng.target = int(logits.argmax(1)[0]) if args.target is None else args.target
     _ENGINE["engine"] = eng
     if not args.masks:
+        from network_interpretation_imagenet_b200.pipeline import AsyncPngWriter, reset_dir
+        reset_dir("./masks")                                     # :469-474
+        os.makedirs("./mask_on_img", exist_ok=True)
+        _ENGINE["writer"] = AsyncPngWriter()
         firstIndex_upperbound = int(0.6 * S)                     # :467
         bounds = np.asarray([[0, firstIndex_upperbound]])
         xp, yp = bayesian_optimisation(n_iters=args.n_iters, sample_loss=sample_loss, val_loader=None, nn_model=model,
                                        criterion=None, bounds=bounds, n_pre_samples=args.n_pre_samples,
                                        random_search=False)      # :479-486
         print("xp", xp.ravel()); print("yp", yp)
+        _ENGINE["writer"].close()
+        bbox_threshold = 180                                     # :491
+        gt = args.gt_bbox if args.gt_bbox is not None else [0, 0, image.shape[2], image.shape[1]]
+        plot_summed_heatmap(args.eval_img_index, bbox_threshold, gt)
     else:
         sels = draw_selections("subset_keep", S, args.n_train + args.n_candidates, seed=args.mask_seed)
         bits = selection_bits(sels, S)

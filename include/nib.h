@@ -95,6 +95,13 @@ int nib_segment_minmax(const float* d_img, const void* d_labels, int label_bytes
 
 int nib_mask_synth(const nib_mask_args* args, void* stream);
 
+/* Display images of the PNG side channel (./mask_on_img/..., bayesian_active_learning_imagenet.py:199-216,
+ * generate_gp_training_data_mnist.py:225-236,:263-269): d_out [N][H][W][C] uint8 =
+ *   KEEP_MUL       uint8 truncation of (x*mask - min) / max * 255 per mask (fp32, the reference's operation order)
+ *   REMOVE_MINMAX  the [0,255] float image `pic`, rounded to nearest as cv2.imwrite does
+ * args->d_seg_minmax is required in both modes; d_out / out_dtype / layout / c_stride / pad_* of args are ignored. */
+int nib_mask_display_u8(const nib_mask_args* args, uint8_t* d_out, void* stream);
+
 /* In-place per-image min-max rescale to [0,255] and the truncated uint8 HWC view (a1):
  * mnist :169-177, cifar :275-283, imagenet :171-178.   d_org [C,H,W] fp32 (overwritten),
  * d_u8 [H,W,C] uint8 (may be NULL). */
@@ -340,6 +347,22 @@ int nib_gp_ei(const double* d_mu, const double* d_sigma, int m, double best,
 int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S,
                 const uint64_t* d_sel, int sel_words, const float* d_y, int N, float* d_heat,
                 void* stream);
+
+/* The heat map is constant on superpixels when its masks are superpixel masks of one label map: d_wseg[s] = sum of d_y[i]
+ * over the masks that select segment s (double, exact for integer labels), d_cover[s] (optional) = how many do.  The
+ * threshold search of generate_gp_training_data_imagenet.py:334-488 works on these S numbers instead of n x n pixels. */
+int nib_segment_weights(const uint64_t* d_sel, int sel_words, const float* d_y, int N, int S, double* d_wseg,
+                        int32_t* d_cover, void* stream);
+
+/* Localisation tail of the heat map (generate_gp_training_data_imagenet.py:519-525, bayesian_active_learning_imagenet.py
+ * :349-377, utils.py:96-109):
+ *   nib_heat_normalize_u8  gray = uint8((H - min(H)) / max(H - min(H)) * 255), float64 arithmetic in numpy's operation
+ *                          order, truncation; d_minmax (optional, double[2]) receives (min, max) of the heat map
+ *   nib_threshold_bbox     cv2.threshold(gray, t, 255, THRESH_BINARY) + findContours(RETR_EXTERNAL) + the boundingRect of
+ *                          largest w*h (OpenCV's order on ties): d_box int32[6] = {x, y, w, h, #components, #pixels > t},
+ *                          zeros when no pixel exceeds t.  H*W <= 65535. */
+int nib_heat_normalize_u8(const float* d_heat, int P, uint8_t* d_gray, double* d_minmax, void* stream);
+int nib_threshold_bbox(const uint8_t* d_gray, int H, int W, int threshold, int32_t* d_box, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pixel-coordinate GP regression on an inducing grid (KISS-GP / SKI) and its training heat map.

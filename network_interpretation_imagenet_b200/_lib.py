@@ -58,6 +58,7 @@ _PROTOTYPES = {
     "nib_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "nib_segment_minmax": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "nib_mask_synth": (_i, [C.POINTER(MaskArgs), _vp]),
+    "nib_mask_display_u8": (_i, [C.POINTER(MaskArgs), _vp, _vp]),
     "nib_prep_minmax_u8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "nib_net_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "nib_net_destroy": (_i, [_vp]),
@@ -103,6 +104,9 @@ _PROTOTYPES = {
     "nib_heatmap_pixels": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "nib_ski_accumulate": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp, _vp]),
     "nib_ski_predict": (_i, [_vp, _i, _d, _d, _i, _d, _vp, _vp, _d, _i, _vp, _vp, _vp]),
+    "nib_segment_weights": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "nib_heat_normalize_u8": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "nib_threshold_bbox": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "nib_vgp_loglik_grad": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nib_vgp_predict": (_i, [_vp, _i, _d, _d, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nib_felzenszwalb": (_i, [_vp, _i, _i, _i, _d, _d, _i, _vp, C.POINTER(_i)]),

@@ -201,6 +201,70 @@ mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels
   }
 }
 
+// ---- display images of the PNG side channel ("next" row 3) ------------------------------------------------------
+// KEEP_MUL (bayesian_active_learning_imagenet.py:199-205, generate_gp_training_data_imagenet.py:250-256 commented):
+//   show = masked.transpose(1,2,0); show -= show.min(); show /= show.max(); show *= 255; show.astype(uint8)   (fp32, truncation)
+// REMOVE_MINMAX (generate_gp_training_data_mnist.py:225-236 `pic`, cifar :316-320): the [0,255] float image the reference
+//   hands to cv2.imwrite, which rounds to nearest when it converts to 8 bits.
+// Per-mask min / max come from the per-segment table like the classifier input's statistics.  Output [N][H][W][C] uint8.
+template <int MODE, typename LabT>
+__global__ void __launch_bounds__(256)
+mask_display_kernel(const float* __restrict__ img, const LabT* __restrict__ labels, const uint64_t* __restrict__ sel,
+                    int words, int N, int C, int H, int W, const float* __restrict__ seg_minmax, int S,
+                    uint8_t* __restrict__ out, int masks_per_cta) {
+  constexpr int kStatChunk = 256;
+  __shared__ float2 s_stats[kStatChunk];
+  const int HW = H * W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < HW;
+  const int lab = active ? (int)labels[p] : 0;
+  float x[kMaxC];
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) x[c] = (c < C && active) ? img[(size_t)c * HW + p] : 0.f;
+  const int n0 = blockIdx.y * masks_per_cta;
+  const int n1 = min(N, n0 + masks_per_cta);
+  for (int n = n0; n < n1; ++n) {
+    const int k = (n - n0) % kStatChunk;
+    if (k == 0) {
+      __syncthreads();
+      const int nn = n + (int)threadIdx.x;
+      if (nn < n1) {
+        if (MODE == NIB_MASK_REMOVE_MINMAX) {
+          s_stats[threadIdx.x] = mask_stats(seg_minmax, sel, words, nn, S);
+        } else {   // min / max of x * mask: extremes of the kept segments, and 0 as soon as one present segment is dropped
+          float mn = INFINITY, mx = -INFINITY;
+          bool any_dropped = false, any = false;
+          for (int s2 = 0; s2 < S; ++s2) {
+            const float smin = seg_minmax[2 * s2], smax = seg_minmax[2 * s2 + 1];
+            if (!(smin <= smax)) continue;
+            any = true;
+            if ((sel[(size_t)nn * words + (s2 >> 6)] >> (s2 & 63)) & 1ull) { mn = fminf(mn, smin); mx = fmaxf(mx, smax); }
+            else any_dropped = true;
+          }
+          if (any_dropped) { mn = fminf(mn, 0.f); mx = fmaxf(mx, 0.f); }
+          if (!any) { mn = 0.f; mx = 0.f; }
+          s_stats[threadIdx.x] = make_float2(mn, __fsub_rn(mx, mn));
+        }
+      }
+      __syncthreads();
+    }
+    if (!active) continue;
+    const bool bit = (sel[(size_t)n * words + (lab >> 6)] >> (lab & 63)) & 1ull;
+    const float2 st = s_stats[k];
+    uint8_t* o = out + ((size_t)n * HW + p) * C;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      if (c >= C) break;
+      float t = (MODE == NIB_MASK_KEEP_MUL) ? __fmul_rn(x[c], bit ? 1.0f : 0.0f) : __fmul_rn(x[c], bit ? 0.0f : 255.0f);
+      t = __fsub_rn(t, st.x);
+      t = __fdiv_rn(t, st.y);
+      t = __fmul_rn(t, 255.0f);
+      if (MODE == NIB_MASK_REMOVE_MINMAX) t = rintf(fminf(fmaxf(t, 0.f), 255.f));   // cv2 saturate_cast<uchar>
+      o[c] = (t == t) ? (uint8_t)t : (uint8_t)0;
+    }
+  }
+}
+
 // zero the halo ring of an NHWC padded batch
 template <typename OutT>
 __global__ void halo_zero_kernel(OutT* out, int N, int H, int W, int c_stride, int pad_h, int pad_w) {
@@ -315,20 +379,28 @@ __global__ void prep_minmax_kernel(float* org, int C, int H, int W, uint8_t* u8)
 
 // ---- heat map --------------------------------------------------------------------------------
 __global__ void heat_weights_kernel(const uint64_t* __restrict__ sel, int words, const float* __restrict__ y,
-                                    int N, int S, double* __restrict__ wseg) {
-  // one block per segment; exact for integer-valued labels (gp_regression.py:82-94 adds ints)
+                                    int N, int S, double* __restrict__ wseg, int* __restrict__ cover) {
+  // one block per segment; exact for integer-valued labels (gp_regression.py:82-94 adds ints).  cover[s] = number of
+  // masks that select segment s (a pixel is a key of the reference's dict_pixel iff some mask covers it)
   const int s = blockIdx.x;
   double acc = 0.0;
+  int cnt = 0;
   for (int n = threadIdx.x; n < N; n += blockDim.x)
-    if ((sel[(size_t)n * words + (s >> 6)] >> (s & 63)) & 1ull) acc += (double)y[n];
+    if ((sel[(size_t)n * words + (s >> 6)] >> (s & 63)) & 1ull) { acc += (double)y[n]; ++cnt; }
   __shared__ double sh[32];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __shared__ int shc[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = acc; shc[threadIdx.x >> 5] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    int c = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { t += sh[i]; c += shc[i]; }
     wseg[s] = t;
+    if (cover) cover[s] = c;
   }
 }
 template <typename LabT>
@@ -450,6 +522,45 @@ int nib_prep_minmax_u8(float* d_org, int C, int H, int W, uint8_t* d_u8, void* s
   return NIB_OK;
 }
 
+int nib_mask_display_u8(const nib_mask_args* a, uint8_t* d_out, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  using namespace nib;
+  NIB_REQUIRE(a && d_out, "nib_mask_display_u8: null pointer");
+  if (a->N == 0) return NIB_OK;
+  NIB_REQUIRE(a->d_img && a->d_labels && a->d_sel && a->d_seg_minmax, "nib_mask_display_u8: null device pointer (d_seg_minmax is required)");
+  NIB_REQUIRE(a->C >= 1 && a->C <= kMaxC && a->H > 0 && a->W > 0 && a->S > 0, "nib_mask_display_u8: bad geometry");
+  NIB_REQUIRE(a->label_bytes == 1 || a->label_bytes == 2, "nib_mask_display_u8: label_bytes must be 1 or 2");
+  NIB_REQUIRE(a->mode == NIB_MASK_KEEP_MUL || a->mode == NIB_MASK_REMOVE_MINMAX, "nib_mask_display_u8: bad mode");
+  const int HW = a->H * a->W;
+  const int gx = ceil_div(HW, 256);
+  int gy = max(1, min(a->N, ceil_div(num_sms() * 16, gx)));
+  const int mpc = ceil_div(a->N, gy);
+  gy = ceil_div(a->N, mpc);
+  dim3 grid(gx, gy);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NIB_DISPLAY(MODE, LABT)                                                                                         \
+  mask_display_kernel<MODE, LABT><<<grid, 256, 0, st>>>(a->d_img, (const LABT*)a->d_labels, a->d_sel, a->sel_words, a->N, \
+                                                        a->C, a->H, a->W, a->d_seg_minmax, a->S, d_out, mpc)
+  if (a->mode == NIB_MASK_KEEP_MUL) {
+    if (a->label_bytes == 1) NIB_DISPLAY(NIB_MASK_KEEP_MUL, uint8_t); else NIB_DISPLAY(NIB_MASK_KEEP_MUL, uint16_t);
+  } else {
+    if (a->label_bytes == 1) NIB_DISPLAY(NIB_MASK_REMOVE_MINMAX, uint8_t); else NIB_DISPLAY(NIB_MASK_REMOVE_MINMAX, uint16_t);
+  }
+#undef NIB_DISPLAY
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+int nib_segment_weights(const uint64_t* d_sel, int sel_words, const float* d_y, int N, int S, double* d_wseg,
+                        int32_t* d_cover, void* stream) {
+  NIB_DEVICE_OR_FAIL();
+  NIB_REQUIRE(d_sel && d_y && d_wseg && N > 0, "nib_segment_weights: bad arguments");
+  NIB_REQUIRE(S > 0 && S <= 4096 && sel_words * 64 >= S, "nib_segment_weights: bad S/sel_words");
+  nib::heat_weights_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(d_sel, sel_words, d_y, N, S, d_wseg, d_cover);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
 int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S, const uint64_t* d_sel,
                 int sel_words, const float* d_y, int N, float* d_heat, void* stream) {
   NIB_DEVICE_OR_FAIL();
@@ -460,7 +571,7 @@ int nib_heatmap(const void* d_labels, int label_bytes, int H, int W, int S, cons
   double* wseg = nullptr;   // per-stream scratch (common.cuh): concurrent heat maps on different streams do not share it
   int rcs = nib::stream_scratch(nib::SCRATCH_HEAT_WSEG, st, sizeof(double) * 4096, sizeof(double) * 4096, reinterpret_cast<void**>(&wseg));
   if (rcs != NIB_OK) return rcs;
-  nib::heat_weights_kernel<<<S, 256, 0, st>>>(d_sel, sel_words, d_y, N, S, wseg);
+  nib::heat_weights_kernel<<<S, 256, 0, st>>>(d_sel, sel_words, d_y, N, S, wseg, nullptr);
   const int HW = H * W;
   if (label_bytes == 1)
     nib::heat_scatter_kernel<uint8_t><<<nib::ceil_div(HW, 256), 256, 0, st>>>((const uint8_t*)d_labels, HW, S, wseg, d_heat);

@@ -184,6 +184,19 @@ class MaskSynth:
         _lib.check(self.lib.nib_mask_synth(C.byref(a), _lib.stream_handle()), "nib_mask_synth")
         return (out, pm) if return_pixel_masks else out
 
+    def display_u8(self, sel_bits, mode: int = KEEP_MUL) -> torch.Tensor:
+        """[N,H,W,C] uint8 display images of the masked inputs, as the reference writes them to ./mask_on_img
+        (bayesian_active_learning_imagenet.py:199-216; mnist :225-236 `pic`)."""
+        d_sel = self.device_bits(sel_bits)
+        N = int(d_sel.shape[0])
+        out = torch.empty(N, self.H, self.W, self.C, dtype=torch.uint8, device=self.device)
+        if N == 0:
+            return out
+        a = self.mask_args(d_sel, mode, None, 0, 0)
+        a.d_seg_minmax = self.seg_minmax().data_ptr()
+        _lib.check(self.lib.nib_mask_display_u8(C.byref(a), out.data_ptr(), _lib.stream_handle()), "nib_mask_display_u8")
+        return out
+
     def heatmap(self, sel_bits, y) -> torch.Tensor:
         """H = sum_i y_i * mask_i over keep-mode masks (gp_regression.py:82-94)."""
         d_sel = self.device_bits(sel_bits)

@@ -16,6 +16,7 @@ Fixtures
   utils.npz            utils.normalize_image / utils.generate_IOU executed on seeded inputs
   ei.npz               BayesianOptimization.expected_improvement on fixed (mu, sigma)
   gp_sklearn.npz       scikit-learn 1.9.0 GaussianProcessRegressor as built at BayesianOptimization.py:154-159
+  localize.npz         generate_gp_training_data_imagenet.py get_pixel_sorted_mask_label / generate_new_mask / heat-map uint8
 """
 from __future__ import annotations
 
@@ -256,6 +257,56 @@ def make_gp_sklearn():
                         mu=mu1, std=std1, lml_opt=m1.log_marginal_likelihood_value_)
 
 
+def make_localize():
+    """generate_gp_training_data_imagenet.py: the function definitions get_pixel_sorted_mask_label (:490-515) and
+    generate_new_mask (:549-565) plus the min-max / uint8 statements of plot_summed_heatmap (:519-525), exec'd on a
+    ./masks directory written in the reference's own format (mask_{i}_{label}.png, 0/255)."""
+    import tempfile
+    import cv2
+    rel = "generate_gp_training_data_imagenet.py"
+    defs1, span1 = _extract(rel, "def load_images_from_folder(folder):", "return img_filenames, labels")
+    defs2, span2 = _extract(rel, "def get_pixel_sorted_mask_label():", "return dict_pixel")
+    defs3, span3 = _extract(rel, "def generate_new_mask(dict_pixel, mask_threshold):", "return result_mask")
+    norm, span4 = _extract(rel, "result_gray_img_show = result_gray_img.copy()",
+                           "result_gray_img_show = np.array(result_gray_img_show, dtype = np.uint8)", after="def plot_summed_heatmap(")
+    n = 24
+    segments = synthetic.voronoi_labels(n, n, 13, seed=4)
+    rng = random.Random(99)
+    S, k = 13, int(0.4 * 13)
+    sels, labels = [], []
+    for _ in range(40):
+        f = rng.randint(1, S - k)
+        sels.append(list(range(f, f + k)))
+        labels.append(rng.randint(0, 1))
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            os.makedirs("masks")
+            for i, (sel, lab) in enumerate(zip(sels, labels)):
+                m = np.isin(segments, sel).astype(np.uint8) * 255
+                cv2.imwrite("masks/mask_{}_{}.png".format(i, lab), m)
+            ns = dict(np=np, os=os, cv2=cv2, n=n)
+            _run(defs1 + "\n" + defs2 + "\n" + defs3, ns)
+            with contextlib.redirect_stdout(io.StringIO()):
+                dict_pixel = ns["get_pixel_sorted_mask_label"]()
+            heat = np.full((n, n), -1.0)
+            for (i, j), v in dict_pixel.items():
+                heat[i, j] = v
+            values = sorted(set(dict_pixel.values()))
+            with contextlib.redirect_stdout(io.StringIO()):
+                new_masks = np.stack([ns["generate_new_mask"](dict_pixel, t) for t in values])
+            dense = np.where(heat >= 0, heat, 0.0)
+            ns2 = dict(np=np, result_gray_img=dense.copy())
+            _run(norm, ns2)
+            gray = ns2["result_gray_img_show"]
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "localize.npz"), segments=segments, sels=np.array(sels, dtype=np.int64),
+                        labels=np.array(labels, dtype=np.int64), heat=heat, values=np.array(values, dtype=np.float64),
+                        new_masks=new_masks, gray=gray, ref_lines=np.array([span1, span2, span3, span4]))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("the reference tree is only present in the build container")
@@ -267,6 +318,7 @@ if __name__ == "__main__":
     make_utils()
     make_ei()
     make_gp_sklearn()
+    make_localize()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
