@@ -396,8 +396,10 @@ def run_ours(args):
     l1, t1 = all_launches()
     ties1 = eng.tie_stats()
     # + per score_local call: score kernel (+ compact, fp32 score, scatter with the tie policy); + one all-gather per step
-    per_call = 1 + (3 if eng.refine_ties is not None else 0)
-    gpu_launches = (l1 - l0) + args.steps * (per_call * len(segments))
+    per_pass = 1 + (3 if eng.refine_ties is not None else 0)
+    win = eng.tie_window if eng.refine_ties is not None else 1 << 30
+    passes = sum((b_ - a_ + win - 1) // win for (_, a_, b_, _) in segments)
+    gpu_launches = (l1 - l0) + args.steps * per_pass * passes
     value = total * args.steps / (ms / 1e3)
 
     for _ in range(2):
@@ -522,6 +524,7 @@ def run_ours(args):
             "config": {"workload": workload, "arch": arch, "masks_per_step_per_gpu": per, "masks_per_step_total": total,
                        "images": n_img, "micro_batch": mb, "streams": args.streams,
                        "refine_ties": eng.refine_ties, "tie_capacity": eng.tie_capacity if eng.refine_ties is not None else None,
+                       "tie_window": eng.tie_window if eng.refine_ties is not None else None,
                        "fused_expand_reduce": os.environ.get("NIB_TC_FUSE", "1") != "0", "sharding": f"masks over {world} ranks",
                        "allgather": "nib_allgather_scores (NCCL from the C ABI)" if world > 1 else None,
                        "weights": "random init, seeded (no network for pretrained weights)", "cuda_graph": bool(args.graph),

@@ -93,15 +93,6 @@ class GPClassificationModel(GridVariationalGPClassifier):
         super().__init__(grid_size=10, grid_bounds=((0.0, float(n)), (0.0, float(n))), const_mean_bounds=(-1e-5, 1e-5),
                          log_lengthscale_bounds=(-5.0, 6.0), log_outputscale_bounds=(-5.0, 6.0))
 
-    def cuda(self):
-        return self
-
-    def train(self):
-        return self
-
-    def eval(self):
-        return self
-
 
 def train(train_x, train_y, model, likelihood):
     model.train()

@@ -201,6 +201,76 @@ mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels
   }
 }
 
+// ---- the classifier's own input layout: NHWC, 4-channel bf16 pixels (8 B) inside a zero halo ---------------------------
+// The tcgen05 stem reads [N][H + 2p][W + 2p][4] bf16.  Writing it pixel by pixel means 8-byte stores (a quarter of each
+// 32 B sector per instruction); here a thread owns TWO 16-byte units = four consecutive padded pixels of the interior rows
+// (row pitch (W + 2p) * 8 B must be a multiple of 16), halo columns included (they are written as +0, which is what they
+// must hold anyway), so every store is a full, aligned 128-bit store.  The top and bottom halo rows are not touched: the
+// buffer owner zeroes them once (net.cu) or halo_zero_kernel does.
+template <int MODE, typename LabT>
+__global__ void __launch_bounds__(256)
+mask_synth_nhwc4_kernel(const float* __restrict__ img, const LabT* __restrict__ labels, const uint64_t* __restrict__ sel,
+                        int words, int N, int C, int H, int W, const float* __restrict__ seg_minmax, int S,
+                        __nv_bfloat16* __restrict__ out, int pad, uint8_t* __restrict__ pixel_mask, int masks_per_cta) {
+  constexpr int kStatChunk = 256;
+  __shared__ float2 s_stats[MODE == NIB_MASK_REMOVE_MINMAX ? kStatChunk : 1];
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const int HW = H * W;
+  const long long total_px = (long long)H * Wp;                 // padded pixels of the interior rows
+  const long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const bool active = q0 < total_px;
+  if (MODE != NIB_MASK_REMOVE_MINMAX && !active) return;
+  int lab[4];
+  bool inside[4];
+  int pix[4];
+  float x[kMaxC][4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const long long q = q0 + v;
+    const int row = (int)(q / Wp), px = (int)(q - (long long)row * Wp);
+    inside[v] = active && q < total_px && px >= pad && px < pad + W;
+    pix[v] = inside[v] ? row * W + (px - pad) : 0;
+    lab[v] = inside[v] ? (int)labels[pix[v]] : 0;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) x[c][v] = (c < C && inside[v]) ? img[(size_t)c * HW + pix[v]] : 0.f;
+  }
+  const int n0 = blockIdx.y * masks_per_cta;
+  const int n1 = min(N, n0 + masks_per_cta);
+  for (int n = n0; n < n1; ++n) {
+    if (MODE == NIB_MASK_REMOVE_MINMAX) {
+      const int k = (n - n0) % kStatChunk;
+      if (k == 0) {
+        __syncthreads();
+        const int nn = n + (int)threadIdx.x;
+        if (nn < n1) s_stats[threadIdx.x] = mask_stats(seg_minmax, sel, words, nn, S);
+        __syncthreads();
+      }
+      if (!active) continue;
+    }
+    float mn = 0.f, mxs = 1.f;
+    if (MODE == NIB_MASK_REMOVE_MINMAX) {
+      const float2 st = s_stats[(n - n0) % kStatChunk];
+      mn = st.x;
+      mxs = st.y;
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const bool bit = (__ldg(sel + (size_t)n * words + (lab[v] >> 6)) >> (lab[v] & 63)) & 1ull;
+      float y[kMaxC];
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) y[c] = (inside[v] && c < C) ? blend<MODE>(x[c][v], bit, mn, mxs) : 0.f;
+      o[2 * v] = pack_bf16x2(y[0], y[1]);
+      o[2 * v + 1] = pack_bf16x2(y[2], y[3]);
+      if (pixel_mask != nullptr && inside[v])
+        pixel_mask[(size_t)n * HW + pix[v]] = (MODE == NIB_MASK_KEEP_MUL) ? (bit ? 1 : 0) : (bit ? 0 : 255);
+    }
+    __nv_bfloat16* dst = out + ((size_t)n * Hp + pad) * Wp * 4 + q0 * 4;
+    st_cs_v4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+    if (q0 + 2 < total_px) st_cs_v4(dst + 8, make_uint4(o[4], o[5], o[6], o[7]));
+  }
+}
+
 // ---- display images of the PNG side channel ("next" row 3) ------------------------------------------------------
 // KEEP_MUL (bayesian_active_learning_imagenet.py:199-205, generate_gp_training_data_imagenet.py:250-256 commented):
 //   show = masked.transpose(1,2,0); show -= show.min(); show /= show.max(); show *= 255; show.astype(uint8)   (fp32, truncation)
@@ -416,6 +486,28 @@ __global__ void heat_scatter_kernel(const LabT* __restrict__ labels, int HW, int
 template <typename OutT, int LAYOUT, int MODE, typename LabT>
 static int launch_mask(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
   const int HW = a->H * a->W;
+  if (LAYOUT == NIB_NHWC && sizeof(OutT) == 2 && a->c_stride == 4 && a->pad_h == a->pad_w && a->pad_w > 0 &&
+      ((a->W + 2 * a->pad_w) % 2) == 0) {
+    // the network input layout: full 128-bit stores over the padded interior rows
+    const long long total_px = (long long)a->H * (a->W + 2 * a->pad_w);
+    const int gx = (int)ceil_div_ll(ceil_div_ll(total_px, 4), 256);
+    int gy = max(1, min(a->N, ceil_div(num_sms() * 16, gx)));
+    const int mpc = ceil_div(a->N, gy);
+    gy = ceil_div(a->N, mpc);
+    mask_synth_nhwc4_kernel<MODE, LabT><<<dim3(gx, gy), 256, 0, st>>>(
+        a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, a->d_seg_minmax, a->S,
+        (__nv_bfloat16*)a->d_out, a->pad_w, a->d_pixel_mask, mpc);
+    NIB_LAUNCH_CHECK();
+    if (!skip_halo) {   // only the top / bottom halo rows remain (the side columns were written above); the generic
+                        // kernel covers them, re-zeroing the sides as well
+      const int Hp = a->H + 2 * a->pad_h, Wp = a->W + 2 * a->pad_w;
+      long long total = (long long)a->N * (Hp * Wp - HW);
+      halo_zero_kernel<OutT><<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
+          (OutT*)a->d_out, a->N, a->H, a->W, a->c_stride, a->pad_h, a->pad_w);
+      NIB_LAUNCH_CHECK();
+    }
+    return NIB_OK;
+  }
   const bool vec4 = (a->W % 4 == 0);
   const int threads = 256;
   const int per = vec4 ? 4 : 1;

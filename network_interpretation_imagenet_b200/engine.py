@@ -22,13 +22,19 @@ from .masks import KEEP_MUL, REMOVE_MINMAX, MaskSynth
 from .scoring import score
 
 # Relative top-2 margin, (top1 - runner-up) / max|logit|, below which a bf16-scored mask is re-scored in fp32.
-# A bf16 arg-max can differ from the fp32 one only if the error of the DIFFERENCE of two logits exceeds their margin.
-# Measured on the bench workload (ResNet-101, 3072 masks, tests/test_gpu_bench_config.py): max |logit error| 4.8e-3 of
-# max|logit|, max error of any (top1 - other) difference 2.9e-3; the default band is that bound with a 2x safety factor,
-# well inside twice the 1e-2 logit tolerance north_star states (which, taken literally as the band, would re-score
-# every mask of a near-tied random-init network: all 3072 margins of the bench workload are below 2e-2).
-DEFAULT_TIE_BAND = 6e-3   # provisional: see tools/r02_diag2.py
-DEFAULT_TIE_CAPACITY = 128
+#
+# A bf16 arg-max differs from the fp32 one only if the error of the DIFFERENCE between the fp32 top-1 and some other logit
+# exceeds that difference, so the band has to cover the largest such error among classes close enough to overtake.
+# Flip study on the bench workload (tools/r02_diag2.py, profiles/r02_flip_study_resnet101.json: ResNet-101, 16384 masks,
+# bf16 micro-batch 384 x 2 streams against the fp32 lowering): row-wise logit error <= 5.7e-3 of max|logit|; error of
+# (top1 - j) over all 1000 classes <= 6.5e-3, over the classes within 2e-2 of the top-1 <= 4.1e-3; 9 of 16384 arg-maxes
+# differ, all at bf16 margins <= 2.35e-3.  The default band sits above both numbers that matter (4.1e-3, 2.35e-3); it
+# re-scores 2.7 % of this workload's masks.  This is a measured bound, not a proof: north_star's 1e-2 logit tolerance taken
+# literally (band 2e-2) would send 99.6 % of the masks of this near-tied random-init network to fp32.  Trained networks
+# have top-2 margins far outside any of these bands and the policy costs them one empty launch sequence (~0.6 ms).
+DEFAULT_TIE_BAND = 4.5e-3
+DEFAULT_TIE_CAPACITY = 256      # rows of the fp32 re-score buffer per window of masks
+DEFAULT_TIE_WINDOW = 4096       # masks scored per tie-policy pass (capacity = 6.25 % of a window)
 
 
 def shard_range(N: int, rank: int, world: int) -> tuple[int, int, int]:
@@ -94,12 +100,14 @@ class PerturbationEngine:
     an fp32 copy of the classifier, so that top-1 equals the reference's on every mask outside numerical noise.
     "auto" (default) = DEFAULT_TIE_BAND for bf16 classifiers lowered from a torch module, off otherwise; None/0 = off.
     The policy runs entirely on the device (no host synchronisation): near-tie rows are compacted into a buffer of
-    `tie_capacity` rows, the fp32 network runs on that buffer with the device-side count as its live batch size, and the
-    refined scores are scattered back.  `tie_stats()` reads the counters (rows refined, rows that did not fit)."""
+    `tie_capacity` rows (per window of `tie_window` masks), the fp32 network runs on that buffer with the device-side
+    count as its live batch size, and the refined scores are scattered back.  `tie_stats()` reads the counters (near-ties
+    found, rows refined, rows that did not fit: overflow > 0 means some near-ties kept their bf16 score)."""
 
     def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
                  max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False,
-                 refine_ties="auto", streams: int = 1, tie_capacity: int = DEFAULT_TIE_CAPACITY):
+                 refine_ties="auto", streams: int = 1, tie_capacity: int = DEFAULT_TIE_CAPACITY,
+                 tie_window: int = DEFAULT_TIE_WINDOW):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.target = int(target)
@@ -117,6 +125,7 @@ class PerturbationEngine:
         if self.refine_ties is not None and self._model_src is None:
             raise ValueError("refine_ties needs the torch module (to lower an fp32 copy), not a lowered Classifier")
         self.tie_capacity = int(tie_capacity)
+        self.tie_window = max(1, int(tie_window))
         self._fp32 = None
         self._tie = None
         self._calls = 0
@@ -212,11 +221,15 @@ class PerturbationEngine:
         if n == 0:
             return out
         self._calls += 1
-        b = self._scratch(n)
-        self.classifier.forward_masked(synth, d_sel, self.mode, out=b["logits"])
-        s = score(b["logits"], self.target, out=b, table=out[:n])
-        if self.refine_ties is not None:
-            self._refine(d_sel, s, out[:n], synth)
+        # windows bound the number of near-ties one pass of the tie policy can meet (its buffer holds tie_capacity rows)
+        win = self.tie_window if self.refine_ties is not None else n
+        for w0 in range(0, n, win):
+            w1 = min(n, w0 + win)
+            b = self._scratch(w1 - w0)
+            self.classifier.forward_masked(synth, d_sel[w0:w1], self.mode, out=b["logits"])
+            s = score(b["logits"], self.target, out=b, table=out[w0:w1])
+            if self.refine_ties is not None:
+                self._refine(d_sel[w0:w1], s, out[w0:w1], synth)
         return out
 
     def gather(self, local: torch.Tensor, N: int, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -47,6 +47,16 @@ class GridVariationalGPClassifier:
         self._d2 = ((U[:, None, :] - U[None, :, :]) ** 2).sum(-1)
         self.history: list[dict] = []
 
+    # gpytorch-module surface the reference's train() / eval_superpixels() call (gp_classification.py:163-164,:226-227)
+    def cuda(self):
+        return self
+
+    def train(self):
+        return self
+
+    def eval(self):
+        return self
+
     # -- state ------------------------------------------------------------------------------------------
     def state_dict(self):
         return {"log_lengthscale": self.log_lengthscale, "log_outputscale": self.log_outputscale, "const_mean": self.const_mean,

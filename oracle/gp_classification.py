@@ -35,7 +35,8 @@ def expected_loglik(mu, s2, y, nodes=64):
     return e, dmu, ds2
 
 
-def elbo_terms(X, y, m, Ls, bounds=(0.0, 224.0), grid_size=10, length_scale=1.0, outputscale=1.0, const_mean=0.0, jitter=1e-6):
+def elbo_terms(X, y, m, Ls, bounds=(0.0, 224.0), grid_size=10, length_scale=1.0, outputscale=1.0, const_mean=0.0, jitter=1e-6,
+               nodes=64):
     """(sum of expected log-likelihoods, KL, grad_m of the data term, grad_S of the data term)."""
     g0, h = make_grid(bounds[0], bounds[1], grid_size)
     K = grid_kernel(g0, h, grid_size, length_scale, outputscale)
@@ -44,7 +45,7 @@ def elbo_terms(X, y, m, Ls, bounds=(0.0, 224.0), grid_size=10, length_scale=1.0,
     S = Ls @ Ls.T
     mu = const_mean + W @ m
     s2 = np.einsum("ij,jk,ik->i", W, S, W)
-    e, dmu, ds2 = expected_loglik(mu, np.maximum(s2, 0.0), np.asarray(y, dtype=np.float64))
+    e, dmu, ds2 = expected_loglik(mu, np.maximum(s2, 0.0), np.asarray(y, dtype=np.float64), nodes=nodes)
     G = K.shape[0]
     Kinv = np.linalg.inv(K)
     kl = 0.5 * (np.trace(Kinv @ S) + m @ Kinv @ m - G + np.linalg.slogdet(K)[1] - np.linalg.slogdet(S)[1])
