@@ -116,7 +116,10 @@ typedef struct nib_net nib_net;
 
 enum nib_precision {
   NIB_PREC_FP32 = 0,  /* fp32 activations/weights, SIMT kernels: the 1e-4 parity mode         */
-  NIB_PREC_BF16 = 1   /* bf16 activations/weights, fp32 accumulate, tcgen05 implicit GEMM     */
+  NIB_PREC_BF16 = 1,  /* bf16 activations/weights, fp32 accumulate, tcgen05 implicit GEMM     */
+  NIB_PREC_X3 = 2     /* fp32 activations; convs with Cin % 16 == 0 multiply split-bf16 operands
+                         (hi*hi + lo*hi + hi*lo) on the tensor cores with fp32 accumulate, ~1e-5 of
+                         the fp32 mode at several times its rate: the tie policy's re-score net  */
 };
 
 /* A network is a flat list of ops over numbered activation buffers (NHWC, per-image geometry

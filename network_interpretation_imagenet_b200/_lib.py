@@ -17,7 +17,7 @@ ABI_VERSION = 2
 MASK_KEEP_MUL, MASK_REMOVE_MINMAX = 0, 1
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_X3 = 0, 1, 2
 CONV_RELU, CONV_PRE_BNRELU = 1, 2
 POOL_MAX, POOL_AVG = 0, 1
 IN_NCHW_F32, IN_NATIVE = 0, 1

@@ -156,7 +156,7 @@ class Classifier:
 
     @staticmethod
     def _from_torch_one(module: nn.Module, input_hw, precision: str, max_batch: int) -> "Classifier":
-        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "x3": _lib.PREC_X3}[precision]
         m = module.module if isinstance(module, nn.DataParallel) else module  # cifar :75 wraps in DataParallel
         if hasattr(m, "layer4") and hasattr(m, "fc") and hasattr(m, "maxpool"):
             return _lower_tv_resnet(m, input_hw or (224, 224), prec, precision, max_batch)

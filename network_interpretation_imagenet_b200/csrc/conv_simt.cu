@@ -13,11 +13,18 @@
 
 namespace nib {
 
-static constexpr int BM = 128, BN = 64, BK = 16;
+static constexpr int BM = 128, BK = 16;
 
-template <typename T>
+// BN x TN: 64 x 4 (8 x 4 outputs per thread) for narrow layers, 128 x 8 (8 x 8 outputs per thread: 64 FMAs per four
+// 128-bit shared loads) for Cout >= 128.  The next K slab's global loads are issued before the FMAs of the current one
+// (register prefetch), so their latency hides behind the arithmetic.  Every output accumulates its products in ascending
+// k with fmaf: results do not depend on the tile shape.
+template <typename T, int BN, int TN>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(ConvParams p) {
+  static_assert(BN == 16 * TN, "16 thread columns of TN outputs");
+  constexpr int BPT = BN * BK / 256;          // weight elements each thread stages per slab (4 or 8), consecutive in k
+  constexpr int B_TPR = BK / BPT;             // threads per weight row (4 or 2)
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Bs[BK][BN];
 
@@ -53,21 +60,22 @@ conv_simt_kernel(ConvParams p) {
   const T* in_img = in + (size_t)an * Hp * Wp * p.in_cstride + p.in_coff;
   const bool cin8 = (p.Cin % 8 == 0) && (p.in_cstride % 8 == 0) && (p.in_coff % 8 == 0);
 
-  // B-load role: cout = tid / 4, 4 consecutive k
-  const int b_co = n0 + (tid >> 2);
-  const int b_k0 = (tid & 3) * 4;
+  // B-load role: cout = tid / B_TPR, BPT consecutive k
+  const int b_row = tid / B_TPR;
+  const int b_co = n0 + b_row;
+  const int b_k0 = (tid % B_TPR) * BPT;
   const bool kvec = (K % 4 == 0);
 
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[8][4];
+  float acc[8][TN];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int kb = 0; kb < K; kb += BK) {
+  float av[8], bv[BPT];
+  auto load_slab = [&](int kb) {
     // ---- gather A ----
-    float av[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) av[j] = 0.f;
     if (a_valid) {
@@ -115,43 +123,56 @@ conv_simt_kernel(ConvParams p) {
       }
     }
     // ---- load B ----
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) bv[j] = 0.f;
     if (b_co < p.Cout) {
       const int k = kb + b_k0;
       const T* src = wgt + (size_t)b_co * K + k;
-      if (kvec && k + 3 < K) {
-        if (sizeof(T) == 2) {
-          uint2 raw = *reinterpret_cast<const uint2*>(src);
-          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) bv[j] = __bfloat162float(h[j]);
+      for (int q = 0; q < BPT; q += 4) {
+        if (kvec && k + q + 3 < K) {
+          if (sizeof(T) == 2) {
+            uint2 raw = *reinterpret_cast<const uint2*>(src + q);
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[q + j] = __bfloat162float(h[j]);
+          } else {
+            float4 f = *reinterpret_cast<const float4*>(src + q);
+            bv[q] = f.x; bv[q + 1] = f.y; bv[q + 2] = f.z; bv[q + 3] = f.w;
+          }
         } else {
-          float4 f = *reinterpret_cast<const float4*>(src);
-          bv[0] = f.x; bv[1] = f.y; bv[2] = f.z; bv[3] = f.w;
-        }
-      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (k + j < K) bv[j] = Elem<T>::ld(src + j);
+          for (int j = 0; j < 4; ++j)
+            if (k + q + j < K) bv[q + j] = Elem<T>::ld(src + q + j);
+        }
       }
     }
-    __syncthreads();  // previous tile fully consumed
+  };
+
+  load_slab(0);
+  for (int kb = 0; kb < K; kb += BK) {
+    __syncthreads();  // previous slab fully consumed
 #pragma unroll
     for (int j = 0; j < 8; ++j) As[a_k0 + j][a_pix] = av[j];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) Bs[b_k0 + j][tid >> 2] = bv[j];
+    for (int j = 0; j < BPT; ++j) Bs[b_k0 + j][b_row] = bv[j];
     __syncthreads();
+    if (kb + BK < K) load_slab(kb + BK);   // in flight while this slab is multiplied
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
       float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bb[4] = {b.x, b.y, b.z, b.w};
+      float bb[TN];
+#pragma unroll
+      for (int q = 0; q < TN; q += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + q]);
+        bb[q] = b.x; bb[q + 1] = b.y; bb[q + 2] = b.z; bb[q + 3] = b.w;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
   }
 
@@ -171,8 +192,8 @@ conv_simt_kernel(ConvParams p) {
     }
     if (res != nullptr) res_row = (size_t)m * p.res_cstride + p.res_coff;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int co = n0 + tx * TN + j;
       if (co >= p.Cout) continue;
       float v = acc[i][j];
       if (p.bias != nullptr) v += p.bias[co];
@@ -184,11 +205,19 @@ conv_simt_kernel(ConvParams p) {
 }
 
 int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st) {
-  dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, BN));
-  if (bf16)
-    conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-  else
-    conv_simt_kernel<float><<<grid, 256, 0, st>>>(p);
+  if (p.Cout >= 128) {
+    dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, 128));
+    if (bf16)
+      conv_simt_kernel<__nv_bfloat16, 128, 8><<<grid, 256, 0, st>>>(p);
+    else
+      conv_simt_kernel<float, 128, 8><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, 64));
+    if (bf16)
+      conv_simt_kernel<__nv_bfloat16, 64, 4><<<grid, 256, 0, st>>>(p);
+    else
+      conv_simt_kernel<float, 64, 4><<<grid, 256, 0, st>>>(p);
+  }
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }

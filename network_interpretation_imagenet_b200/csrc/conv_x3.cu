@@ -1,0 +1,227 @@
+// conv_x3.cu — fp32-grade implicit-GEMM convolution on the tensor cores: split-bf16 ("bf16x3") products, fp32 accumulate.
+//
+// Role: the re-score path of the bf16 tie policy (score.cu) and the fast variant of the fp32 parity mode.  Activations and
+// outputs are fp32 NHWC exactly as in the CUDA-core mode (conv_simt.cu); each fp32 operand is split on the fly into
+//     x = hi + lo,   hi = bf16(x),   lo = bf16(x - hi)            (16 mantissa bits between them)
+// and the product is accumulated in fp32 as  hi_a*hi_w + lo_a*hi_w + hi_a*lo_w  (the lo*lo term, ~2^-18 relative, is
+// dropped).  Three mma.sync.m16n8k16.bf16 per output tile and k-step instead of one: ~1e-5 relative to an fp32 FMA chain,
+// at several times the CUDA-core kernel's rate.  Weights arrive pre-split (two bf16 KRSC arrays, net.cu).
+//
+//   out[m, co] = act( sum_{r,s,c} pre(in[n, p*st-pad+r, q*st-pad+s, c]) * w[co, r, s, c] + bias[co] + residual[m, co] )
+//
+// CTA: 256 threads, tile 128 pixels x BN couts x 32 k; warp tile (128 / WARPS_M) x 32.  Operands are staged in shared
+// memory as bf16 rows of 32 k padded to 40 elements (80 B: the 8 rows of an ldmatrix phase fall into distinct banks);
+// the next slab's global loads are issued before the MMAs of the current one.  Needs Cin % 16 == 0 (a 16-element k run
+// stays inside one filter tap); the stems (Cin = 1 / 3) stay on conv_simt_kernel.
+// Same reference call sites as conv_simt.cu: `model(masked_img_tensor)`, generate_gp_training_data_imagenet.py:246.
+#include "common.cuh"
+#include "layers.cuh"
+
+namespace nib {
+
+static constexpr int X3_BM = 128, X3_BK = 32, X3_LD = 40;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (hi, lo) bf16 pair of two consecutive fp32 values, packed low element first
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 2)
+conv_x3_kernel(ConvParams p, const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo) {
+  constexpr int WARPS_M = BN == 128 ? 2 : 4;
+  constexpr int WM = X3_BM / WARPS_M;          // 64 or 32 rows per warp
+  constexpr int MT = WM / 16;                  // m16 tiles per warp
+  constexpr int NT = 4;                        // n8 tiles per warp (32 columns)
+  constexpr int B_ELEMS = BN * X3_BK / 256;    // weight elements per thread, slab and array (16 or 8)
+  constexpr int B_TPR = X3_BK / B_ELEMS;       // threads per weight row (2 or 4)
+  __shared__ __align__(16) __nv_bfloat16 Ah[X3_BM * X3_LD], Al[X3_BM * X3_LD], Bh[BN * X3_LD], Bl[BN * X3_LD];
+
+  const float* __restrict__ in = reinterpret_cast<const float*>(p.in);
+  float* __restrict__ out = reinterpret_cast<float*>(p.out);
+  const float* __restrict__ res = reinterpret_cast<const float*>(p.res);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * X3_BM;
+  const int n0 = blockIdx.y * BN;
+  const int K = p.R * p.S * p.Cin;
+  if (p.dyn_n != nullptr) {   // device-side live batch (tie policy): whole blocks beyond it leave before the first barrier
+    const long long live = (long long)max(*p.dyn_n, 0) * p.P * p.Q;
+    if (live < p.M) p.M = (int)live;
+    if (m0 >= p.M) return;
+  }
+
+  // A-load role: pixel tid % 128, 16 consecutive k starting at (tid / 128) * 16 of the slab
+  const int a_pix = tid & (X3_BM - 1);
+  const int a_k0 = (tid >> 7) * 16;
+  const int am = m0 + a_pix;
+  const bool a_valid = am < p.M;
+  int an = 0, ap = 0, aq = 0;
+  if (a_valid) {
+    an = am / (p.P * p.Q);
+    const int rem = am - an * p.P * p.Q;
+    ap = rem / p.Q;
+    aq = rem - ap * p.Q;
+  }
+  const int ih0 = ap * p.stride - p.pad, iw0 = aq * p.stride - p.pad;
+  const int Hp = p.Hin + 2 * p.in_halo, Wp = p.Win + 2 * p.in_halo;
+  const float* in_img = in + (size_t)an * Hp * Wp * p.in_cstride + p.in_coff;
+
+  // B-load role: weight row tid / B_TPR, B_ELEMS consecutive k
+  const int b_row = tid / B_TPR;
+  const int b_co = n0 + b_row;
+  const int b_k0 = (tid % B_TPR) * B_ELEMS;
+
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  float av[16];
+  uint4 bh[B_ELEMS / 8], bl[B_ELEMS / 8];
+  auto load_slab = [&](int kb) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) av[j] = 0.f;
+    const int k = kb + a_k0;
+    if (a_valid && k < K) {
+      const int tap = k / p.Cin, c = k - tap * p.Cin;
+      const int r = tap / p.S, s = tap - r * p.S;
+      const int ih = ih0 + r, iw = iw0 + s;
+      if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win) {
+        const float* src = in_img + ((size_t)(ih + p.in_halo) * Wp + (iw + p.in_halo)) * p.in_cstride + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 f = *reinterpret_cast<const float4*>(src + 4 * q);
+          av[4 * q] = f.x; av[4 * q + 1] = f.y; av[4 * q + 2] = f.z; av[4 * q + 3] = f.w;
+        }
+        if (p.pre_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) av[j] = fmaxf(fmaf(av[j], p.pre_scale[c + j], p.pre_shift[c + j]), 0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < B_ELEMS / 8; ++q) {
+      bh[q] = make_uint4(0u, 0u, 0u, 0u);
+      bl[q] = make_uint4(0u, 0u, 0u, 0u);
+      const int kk = kb + b_k0 + 8 * q;
+      if (b_co < p.Cout && kk < K) {
+        bh[q] = *reinterpret_cast<const uint4*>(w_hi + (size_t)b_co * K + kk);
+        bl[q] = *reinterpret_cast<const uint4*>(w_lo + (size_t)b_co * K + kk);
+      }
+    }
+  };
+
+  const uint32_t ah_s = (uint32_t)__cvta_generic_to_shared(Ah), al_s = (uint32_t)__cvta_generic_to_shared(Al);
+  const uint32_t bh_s = (uint32_t)__cvta_generic_to_shared(Bh), bl_s = (uint32_t)__cvta_generic_to_shared(Bl);
+  // ldmatrix lane addresses (bytes) inside a 16 x 16 A tile / a 16(n) x 16(k) pair of B tiles
+  const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * X3_LD + (lane >> 4) * 8) * 2u;
+  const uint32_t b_lane = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * X3_LD + ((lane >> 3) & 1) * 8) * 2u;
+
+  load_slab(0);
+  for (int kb = 0; kb < K; kb += X3_BK) {
+    __syncthreads();   // the previous slab has been consumed
+    {
+      uint32_t h[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split2(av[2 * j], av[2 * j + 1], h[j], l[j]);
+      uint4* dh = reinterpret_cast<uint4*>(Ah + a_pix * X3_LD + a_k0);
+      uint4* dl = reinterpret_cast<uint4*>(Al + a_pix * X3_LD + a_k0);
+      dh[0] = make_uint4(h[0], h[1], h[2], h[3]); dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+      dl[0] = make_uint4(l[0], l[1], l[2], l[3]); dl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+#pragma unroll
+      for (int q = 0; q < B_ELEMS / 8; ++q) {
+        *reinterpret_cast<uint4*>(Bh + b_row * X3_LD + b_k0 + 8 * q) = bh[q];
+        *reinterpret_cast<uint4*>(Bl + b_row * X3_LD + b_k0 + 8 * q) = bl[q];
+      }
+    }
+    __syncthreads();
+    if (kb + X3_BK < K) load_slab(kb + X3_BK);   // in flight while this slab is multiplied
+#pragma unroll
+    for (int ks = 0; ks < X3_BK; ks += 16) {
+      uint32_t fbh[NT][2], fbl[NT][2];
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        const uint32_t off = (uint32_t)((wn * 32 + np * 16) * X3_LD + ks) * 2u + b_lane;
+        uint32_t r[4];
+        ldsm_x4(r, bh_s + off);
+        fbh[2 * np][0] = r[0]; fbh[2 * np][1] = r[1]; fbh[2 * np + 1][0] = r[2]; fbh[2 * np + 1][1] = r[3];
+        ldsm_x4(r, bl_s + off);
+        fbl[2 * np][0] = r[0]; fbl[2 * np][1] = r[1]; fbl[2 * np + 1][0] = r[2]; fbl[2 * np + 1][1] = r[3];
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t off = (uint32_t)((wm * WM + mt * 16) * X3_LD + ks) * 2u + a_lane;
+        uint32_t fah[4], fal[4];
+        ldsm_x4(fah, ah_s + off);
+        ldsm_x4(fal, al_s + off);
+        // small terms first; each pass walks the four accumulators so dependent MMAs are four issues apart
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], fal, fbh[nt][0], fbh[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], fah, fbl[nt][0], fbl[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], fah, fbh[nt][0], fbh[nt][1]);
+      }
+    }
+  }
+
+  // ---- epilogue: accumulator fragment (row = lane / 4 (+8), columns 2 * (lane % 4) + {0, 1}) ----
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = m0 + wm * WM + mt * 16 + (lane >> 2) + half * 8;
+      if (m >= p.M) continue;
+      const size_t out_row = (size_t)m * p.out_cstride + p.out_coff;
+      const size_t res_row = (size_t)m * p.res_cstride + p.res_coff;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int co = n0 + wn * 32 + nt * 8 + (lane & 3) * 2 + e;
+          if (co >= p.Cout) continue;
+          float v = acc[mt][nt][half * 2 + e];
+          if (p.bias != nullptr) v += p.bias[co];
+          if (res != nullptr && co < p.res_C) v += res[res_row + co];
+          if (p.relu) v = fmaxf(v, 0.f);
+          out[out_row + co] = v;
+        }
+    }
+}
+
+bool conv_x3_supported(const ConvParams& p) {
+  return p.Cin % 16 == 0 && p.in_cstride % 4 == 0 && p.in_coff % 4 == 0 && p.out_halo == 0;
+}
+
+int launch_conv_x3(const ConvParams& p, const void* w_hi, const void* w_lo, cudaStream_t st) {
+  const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(w_hi);
+  const __nv_bfloat16* wl = reinterpret_cast<const __nv_bfloat16*>(w_lo);
+  if (p.Cout >= 128) {
+    dim3 grid(ceil_div(p.M, X3_BM), ceil_div(p.Cout, 128));
+    conv_x3_kernel<128><<<grid, 256, 0, st>>>(p, wh, wl);
+  } else {
+    dim3 grid(ceil_div(p.M, X3_BM), ceil_div(p.Cout, 64));
+    conv_x3_kernel<64><<<grid, 256, 0, st>>>(p, wh, wl);
+  }
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
+}  // namespace nib

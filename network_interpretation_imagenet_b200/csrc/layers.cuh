@@ -35,6 +35,9 @@ struct PoolParams {
 };
 
 int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st);
+// split-bf16 tensor-core conv on fp32 activations (conv_x3.cu); w_hi / w_lo: bf16 KRSC halves of the fp32 weights
+bool conv_x3_supported(const ConvParams& p);
+int launch_conv_x3(const ConvParams& p, const void* w_hi, const void* w_lo, cudaStream_t st);
 int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st);
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
               int Cout, float* logits, const int* dyn_n, cudaStream_t st);

@@ -29,6 +29,8 @@ struct NetOp {
   float* d_pre_shift;
   void* d_w_pack;     // pre-activation convs in bf16 nets: KRSC weights with Cin zero-padded to a multiple of 64
   int pack_cin;       // that padded Cin (0: no packed tensor-core path for this op)
+  void* d_w_hi;       // NIB_PREC_X3: bf16 split of the fp32 KRSC weights, w = hi + lo (conv_x3.cu)
+  void* d_w_lo;
   TcConvPlan* plan;
   // 1x1 expansion fused with the next op (the following bottleneck's 1x1 reduction): this op launches both, the next op
   // carries fused_skip.  next_* is a copy of what the launch needs from that op (the profiler runs ops one at a time).
@@ -47,6 +49,7 @@ struct nib_net {
   int precision;
   int max_batch;
   bool bf16;
+  bool x3;                    // fp32 activations, split-bf16 tensor-core products for the convs that qualify
   std::vector<NetBuffer> bufs;
   std::vector<NetOp> ops;
   void* pack_scratch;        // [max_batch * H * W][pack_cin] bf16: relu(bn(x)) of the conv being run (largest such layer)
@@ -57,7 +60,7 @@ struct nib_net {
   bool use_tc;
   bool use_graph;
   const int* dyn_n;           // device-side live batch size for the CUDA-core kernels (fp32 nets), or null
-  long long launches, tc_launches;
+  long long launches, tc_launches, x3_launches;
   // CUDA graphs of the op list, one per batch size: the graph reads the net's own input buffer and writes the net's own
   // logits buffer (staging the caller's input and copying the logits out happen outside it), so caller pointers are not
   // part of the key and the cache is bounded by the number of distinct batch sizes (at most kMaxGraphs, then flushed).
@@ -90,11 +93,13 @@ extern "C" {
 int nib_net_create(int precision, int max_batch, nib_net** out) {
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(out != nullptr, "nib_net_create: null out");
-  NIB_REQUIRE(precision == NIB_PREC_FP32 || precision == NIB_PREC_BF16, "nib_net_create: bad precision %d", precision);
+  NIB_REQUIRE(precision == NIB_PREC_FP32 || precision == NIB_PREC_BF16 || precision == NIB_PREC_X3,
+              "nib_net_create: bad precision %d", precision);
   NIB_REQUIRE(max_batch > 0, "nib_net_create: max_batch must be > 0");
   nib_net* n = new nib_net();
   n->precision = precision;
   n->bf16 = precision == NIB_PREC_BF16;
+  n->x3 = precision == NIB_PREC_X3;
   n->max_batch = max_batch;
   n->input_buf = -1;
   n->pack_scratch = nullptr;
@@ -105,7 +110,7 @@ int nib_net_create(int precision, int max_batch, nib_net** out) {
   n->use_graph = false;
   n->dyn_n = nullptr;
   n->graph_logits = nullptr;
-  n->launches = n->tc_launches = 0;
+  n->launches = n->tc_launches = n->x3_launches = 0;
   *out = n;
   return NIB_OK;
 }
@@ -121,6 +126,8 @@ int nib_net_destroy(nib_net* net) {
     if (o.d_w) cudaFree(o.d_w);
     if (o.d_w_pack) cudaFree(o.d_w_pack);
     if (o.d_w_alt) cudaFree(o.d_w_alt);
+    if (o.d_w_hi) cudaFree(o.d_w_hi);
+    if (o.d_w_lo) cudaFree(o.d_w_lo);
     if (o.d_bias) cudaFree(o.d_bias);
     if (o.d_pre_scale) cudaFree(o.d_pre_scale);
     if (o.d_pre_shift) cudaFree(o.d_pre_shift);
@@ -190,6 +197,20 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
   } else {
     NIB_CUDA(cudaMalloc(&op.d_w, nel * 4 + 256));
     NIB_CUDA(cudaMemcpy(op.d_w, krsc.data(), nel * 4, cudaMemcpyHostToDevice));
+    if (net->x3 && d->Cin % 16 == 0) {   // w = hi + lo with hi = bf16(w), lo = bf16(w - hi)
+      std::vector<uint16_t> hi(nel), lo(nel);
+      for (size_t i = 0; i < nel; ++i) {
+        hi[i] = f32_to_bf16_rn(krsc[i]);
+        uint32_t u = (uint32_t)hi[i] << 16;
+        float hf;
+        memcpy(&hf, &u, 4);
+        lo[i] = f32_to_bf16_rn(krsc[i] - hf);
+      }
+      NIB_CUDA(cudaMalloc(&op.d_w_hi, nel * 2 + 256));
+      NIB_CUDA(cudaMalloc(&op.d_w_lo, nel * 2 + 256));
+      NIB_CUDA(cudaMemcpy(op.d_w_hi, hi.data(), nel * 2, cudaMemcpyHostToDevice));
+      NIB_CUDA(cudaMemcpy(op.d_w_lo, lo.data(), nel * 2, cudaMemcpyHostToDevice));
+    }
   }
   if (net->bf16 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Cin <= 4 && bi.C == 4 && bi.pad == 3) {
     // 4-channel pixels: K block kb = filter rows (2kb, 2kb+1), each (7 taps + 1 filler) x 4 channels; row 7 is zero
@@ -414,6 +435,9 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
       } else if (op.plan && net->use_tc) {
         rc = tc_conv_launch(op.plan, p, st);
         net->tc_launches++;
+      } else if (net->x3 && op.d_w_hi && conv_x3_supported(p)) {
+        rc = launch_conv_x3(p, op.d_w_hi, op.d_w_lo, st);
+        net->x3_launches++;
       } else {
         rc = launch_conv_simt(p, net->bf16, st);
       }
@@ -634,7 +658,7 @@ int nib_net_set_tensor_core(nib_net* net, int enable) {
 
 int nib_net_set_dynamic_batch(nib_net* net, const int32_t* d_count) {
   NIB_REQUIRE(net != nullptr, "nib_net_set_dynamic_batch: null handle");
-  NIB_REQUIRE(d_count == nullptr || !net->bf16, "nib_net_set_dynamic_batch: only fp32 (CUDA-core) networks honour a device-side batch size");
+  NIB_REQUIRE(d_count == nullptr || !net->bf16, "nib_net_set_dynamic_batch: only fp32 / x3 networks honour a device-side batch size");
   net->dyn_n = d_count;
   for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
   net->graphs.clear();

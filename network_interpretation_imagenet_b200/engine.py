@@ -97,7 +97,9 @@ class ScoreComm:
 
 class PerturbationEngine:
     """refine_ties: relative top-2 margin (top1 - runner-up) / max|logit| below which a bf16-scored mask is re-scored by
-    an fp32 copy of the classifier, so that top-1 equals the reference's on every mask outside numerical noise.
+    an fp32-grade copy of the classifier (`tie_precision`: "x3" = fp32 activations with split-bf16 tensor-core products,
+    within ~1e-5 of the fp32 lowering at several times its rate; "fp32" = the CUDA-core lowering itself), so that top-1
+    equals the reference's on every mask outside numerical noise.
     "auto" (default) = DEFAULT_TIE_BAND for bf16 classifiers lowered from a torch module, off otherwise; None/0 = off.
     The policy runs entirely on the device (no host synchronisation): near-tie rows are compacted into a buffer of
     `tie_capacity` rows (per window of `tie_window` masks), the fp32 network runs on that buffer with the device-side
@@ -107,7 +109,7 @@ class PerturbationEngine:
     def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
                  max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False,
                  refine_ties="auto", streams: int = 1, tie_capacity: int = DEFAULT_TIE_CAPACITY,
-                 tie_window: int = DEFAULT_TIE_WINDOW):
+                 tie_window: int = DEFAULT_TIE_WINDOW, tie_precision: str = "x3"):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.target = int(target)
@@ -126,6 +128,9 @@ class PerturbationEngine:
             raise ValueError("refine_ties needs the torch module (to lower an fp32 copy), not a lowered Classifier")
         self.tie_capacity = int(tie_capacity)
         self.tie_window = max(1, int(tie_window))
+        if tie_precision not in ("x3", "fp32"):
+            raise ValueError("tie_precision must be 'x3' (split-bf16 tensor-core products, fp32 accumulate) or 'fp32' (CUDA cores)")
+        self.tie_precision = tie_precision
         self._fp32 = None
         self._tie = None
         self._calls = 0
@@ -139,7 +144,7 @@ class PerturbationEngine:
     # -- tie policy ------------------------------------------------------------------------------------
     def _fp32_classifier(self) -> Classifier:
         if self._fp32 is None:
-            self._fp32 = Classifier.from_torch(self._model_src, (self.synth.H, self.synth.W), precision="fp32",
+            self._fp32 = Classifier.from_torch(self._model_src, (self.synth.H, self.synth.W), precision=self.tie_precision,
                                                max_batch=self.tie_capacity)
         return self._fp32
 

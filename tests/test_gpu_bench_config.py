@@ -107,7 +107,7 @@ def test_tie_policy_is_device_side_and_bounded(bench_setup):
     nib = s["nib"]
     from network_interpretation_imagenet_b200.classifier import Classifier
     eng = nib.PerturbationEngine(s["model"], s["x"], s["seg"], target=0, mode=nib.KEEP_MUL, precision="bf16", max_batch=64,
-                                 S=50, refine_ties=10.0, tie_capacity=16)
+                                 S=50, refine_ties=10.0, tie_capacity=16, tie_precision="fp32")
     bits = s["bits"][:48]
     out = eng.score_masks(bits)
     st = eng.tie_stats()
@@ -118,6 +118,14 @@ def test_tie_policy_is_device_side_and_bounded(bench_setup):
     assert torch.equal(out["target_prob"][:16], s32["target_prob"]) and torch.equal(out["top1"][:16], s32["top1"])
     s16 = nib.score(eng.classifier.forward_masked(eng.synth, d_bits, nib.KEEP_MUL), 0)
     assert torch.equal(out["target_prob"][16:], s16["target_prob"][16:]) and torch.equal(out["top1"][16:], s16["top1"][16:])
+    # the default re-score precision (split-bf16 tensor-core products): same rows refined, scores within 1e-4 of the fp32 ones
+    engx = nib.PerturbationEngine(s["model"], s["x"], s["seg"], target=0, mode=nib.KEEP_MUL, precision="bf16", max_batch=64,
+                                  S=50, refine_ties=10.0, tie_capacity=16)
+    assert engx.tie_precision == "x3"
+    outx = engx.score_masks(bits)
+    assert torch.equal(outx["top1"][:16], s32["top1"])
+    assert torch.allclose(outx["target_prob"][:16], s32["target_prob"], rtol=1e-4, atol=0)
+    assert torch.equal(outx["target_prob"][16:], s16["target_prob"][16:])
     # no near-tie at all: nothing is refined, nothing changes
     eng0 = nib.PerturbationEngine(s["model"], s["x"], s["seg"], target=0, mode=nib.KEEP_MUL, precision="bf16", max_batch=64,
                                   S=50, refine_ties=1e-9, tie_capacity=16)

@@ -57,7 +57,7 @@ def _one_conv_net(nib, precision, Cin, Cout, k, stride, pad, H, W, relu, residua
     w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
     bias = torch.randn(Cout, generator=g) * 0.1
     x = torch.randn(N, Cin, H, W, generator=g)
-    b = _Builder({"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision], N)
+    b = _Builder({"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "x3": _lib.PREC_X3}[precision], N)
     x_in = b.buffer(H, W, Cin, pooled=False)
     Ho, Wo = _out_hw(H, k, stride, pad), _out_hw(W, k, stride, pad)
     res_buf = None
@@ -128,6 +128,30 @@ def test_conv_simt_vs_torch(nib, precision, case):
     err = (got - ref).abs().max().item()
     scale = max(ref.abs().max().item(), 1.0)
     assert err <= (1e-5 if precision == "fp32" else 1.2e-2) * scale
+
+
+X3_CASES = [
+    # Cin, Cout, k, stride, pad, H,  W,  relu, residual
+    (16, 16, 3, 1, 1, 32, 32, True, True),       # ResNet-56 stage 1 (K = 144: half a slab of tail)
+    (32, 64, 3, 2, 1, 16, 16, True, False),
+    (64, 256, 1, 1, 0, 14, 14, False, True),
+    (256, 64, 1, 1, 0, 9, 9, True, False),
+    (256, 256, 3, 1, 1, 14, 14, True, False),
+    (512, 1000, 1, 1, 0, 3, 3, False, False),    # ragged Cout: 1000 = 7 x 128 + 104
+    (128, 32, 3, 1, 1, 7, 7, False, False),
+]
+
+
+@pytest.mark.parametrize("case", X3_CASES, ids=lambda c: "cin%d_cout%d_k%d_s%d_h%d" % (c[0], c[1], c[2], c[3], c[5]))
+def test_conv_x3_vs_torch(nib, case):
+    """Split-bf16 tensor-core conv (conv_x3.cu): fp32 in / out, products hi*hi + lo*hi + hi*lo, against torch fp64."""
+    Cin, Cout, k, stride, pad, H, W, relu, residual = case
+    got, ref, net = _one_conv_net(nib, "x3", Cin, Cout, k, stride, pad, H, W, relu, residual, N=5, seed=sum(case[:7]))
+    err = (got - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    assert err <= 2e-5 * scale, f"max abs err {err} (scale {scale})"
+    got32, _, _ = _one_conv_net(nib, "fp32", Cin, Cout, k, stride, pad, H, W, relu, residual, N=5, seed=sum(case[:7]))
+    assert (got - got32).abs().max().item() <= 2e-5 * scale
 
 
 @pytest.mark.parametrize("cpix", [8, 4])
@@ -259,6 +283,28 @@ def test_resnet56_bf16_is_outside_the_stated_tolerance_and_says_so(nib):
     srt = np.sort(want, 1)
     safe = (srt[:, -1] - srt[:, -2]) > 2 * RESNET56_BF16_MEASURED_TOL * np.abs(want).max(axis=1)
     assert np.array_equal(got.argmax(1)[safe], want.argmax(1)[safe])
+
+
+def test_x3_mode_whole_networks(nib):
+    """The tie policy's re-score precision: every network within the fp32 tolerance (1e-4) of the torch fp32 forward, and
+    within 5e-5 of the CUDA-core fp32 lowering."""
+    m = ocls.build_imagenet_model("resnet101")
+    x = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(3, 1, 1, 1)
+    x[1] = x[1].flip(2) * 0.5
+    x[2] = x[2] * (torch.rand(1, 224, 224, generator=torch.Generator().manual_seed(3)) > 0.5).float()
+    net, got, want = _check_net(nib, m, x, "x3", TOL_FP32)
+    ref32 = nib.Classifier.from_torch(m, (224, 224), precision="fp32", max_batch=3).forward(x.cuda()).cpu().numpy()
+    assert rel_err(got, ref32) <= 5e-5
+    assert np.array_equal(got.argmax(1), ref32.argmax(1))
+    m56 = ocls.load_resnet56()
+    x56 = torch.rand(32, 3, 32, 32, generator=torch.Generator().manual_seed(9))
+    _check_net(nib, m56, x56, "x3", TOL_FP32, max_batch=16)
+    mm = ocls.load_mnist_net()
+    _check_net(nib, mm, torch.rand(16, 1, 28, 28, generator=torch.Generator().manual_seed(3)), "x3", TOL_FP32)
+    md = ocls.build_imagenet_model("densenet121")
+    xd = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(2, 1, 1, 1)
+    xd[1] = xd[1].flip(1)
+    _check_net(nib, md, xd, "x3", TOL_FP32)
 
 
 def test_resnet101_fp32(nib):
