@@ -10,8 +10,9 @@
 //   out[m, co] = act( sum_{r,s,c} pre(in[n, p*st-pad+r, q*st-pad+s, c]) * w[co, r, s, c] + bias[co] + residual[m, co] )
 //
 // CTA: 256 threads, tile 128 pixels x BN couts x 32 k; warp tile (128 / WARPS_M) x 32.  Operands are staged in shared
-// memory as bf16 rows of 32 k padded to 40 elements (80 B: the 8 rows of an ldmatrix phase fall into distinct banks);
-// the next slab's global loads are issued before the MMAs of the current one.  Needs Cin % 16 == 0 (a 16-element k run
+// memory as bf16 rows of 32 k padded to 40 elements (80 B: the 8 rows of an ldmatrix phase fall into distinct banks).
+// Weights stream through a 4-stage cp.async ring (three slabs in flight); the next activation slab's global loads are
+// issued before the MMAs of the current one and split into hi / lo on their way into shared memory.  Needs Cin % 16 == 0 (a 16-element k run
 // stays inside one filter tap); the stems (Cin = 1 / 3) stay on conv_simt_kernel.
 // Same reference call sites as conv_simt.cu: `model(masked_img_tensor)`, generate_gp_training_data_imagenet.py:246.
 #include "common.cuh"
@@ -20,6 +21,16 @@
 namespace nib {
 
 static constexpr int X3_BM = 128, X3_BK = 32, X3_LD = 40;
+static constexpr int X3_STAGES = 4;   // weight slabs in flight (cp.async ring): the weights of a 100-layer network do not
+                                      // stay in L2 between forwards, and at the tie policy's batch sizes (tens of images,
+                                      // < 1 wave of CTAs) one DRAM round trip per slab was the whole kernel time
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -47,7 +58,11 @@ conv_x3_kernel(ConvParams p, const __nv_bfloat16* __restrict__ w_hi, const __nv_
   constexpr int NT = 4;                        // n8 tiles per warp (32 columns)
   constexpr int B_ELEMS = BN * X3_BK / 256;    // weight elements per thread, slab and array (16 or 8)
   constexpr int B_TPR = X3_BK / B_ELEMS;       // threads per weight row (2 or 4)
-  __shared__ __align__(16) __nv_bfloat16 Ah[X3_BM * X3_LD], Al[X3_BM * X3_LD], Bh[BN * X3_LD], Bl[BN * X3_LD];
+  constexpr int A_ELEMS = X3_BM * X3_LD, B_STAGE = BN * X3_LD;   // elements per array
+  extern __shared__ __align__(16) __nv_bfloat16 x3_smem[];
+  __nv_bfloat16* Ah = x3_smem;
+  __nv_bfloat16* Al = x3_smem + A_ELEMS;
+  __nv_bfloat16* Bring = x3_smem + 2 * A_ELEMS;                   // [stage][hi | lo][BN * X3_LD]
 
   const float* __restrict__ in = reinterpret_cast<const float*>(p.in);
   float* __restrict__ out = reinterpret_cast<float*>(p.out);
@@ -94,7 +109,19 @@ conv_x3_kernel(ConvParams p, const __nv_bfloat16* __restrict__ w_hi, const __nv_
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
   float av[16];
-  uint4 bh[B_ELEMS / 8], bl[B_ELEMS / 8];
+  const uint32_t bring_s = (uint32_t)__cvta_generic_to_shared(Bring);
+  // this thread's share of one weight slab (hi and lo), asynchronously into ring stage `stage`; zero-filled past Cout / K
+  auto issue_b = [&](int stage, int kb) {
+#pragma unroll
+    for (int q = 0; q < B_ELEMS / 8; ++q) {
+      const int kk = kb + b_k0 + 8 * q;
+      const bool ok = b_co < p.Cout && kk < K;
+      const size_t off = ok ? (size_t)b_co * K + kk : 0;
+      const uint32_t dst = bring_s + (uint32_t)((stage * 2 * B_STAGE + b_row * X3_LD + b_k0 + 8 * q) * 2);
+      cp_async16(dst, w_hi + off, ok ? 16 : 0);
+      cp_async16(dst + (uint32_t)(B_STAGE * 2), w_lo + off, ok ? 16 : 0);
+    }
+  };
   auto load_slab = [&](int kb) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) av[j] = 0.f;
@@ -116,27 +143,23 @@ conv_x3_kernel(ConvParams p, const __nv_bfloat16* __restrict__ w_hi, const __nv_
         }
       }
     }
-#pragma unroll
-    for (int q = 0; q < B_ELEMS / 8; ++q) {
-      bh[q] = make_uint4(0u, 0u, 0u, 0u);
-      bl[q] = make_uint4(0u, 0u, 0u, 0u);
-      const int kk = kb + b_k0 + 8 * q;
-      if (b_co < p.Cout && kk < K) {
-        bh[q] = *reinterpret_cast<const uint4*>(w_hi + (size_t)b_co * K + kk);
-        bl[q] = *reinterpret_cast<const uint4*>(w_lo + (size_t)b_co * K + kk);
-      }
-    }
   };
 
   const uint32_t ah_s = (uint32_t)__cvta_generic_to_shared(Ah), al_s = (uint32_t)__cvta_generic_to_shared(Al);
-  const uint32_t bh_s = (uint32_t)__cvta_generic_to_shared(Bh), bl_s = (uint32_t)__cvta_generic_to_shared(Bl);
   // ldmatrix lane addresses (bytes) inside a 16 x 16 A tile / a 16(n) x 16(k) pair of B tiles
   const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * X3_LD + (lane >> 4) * 8) * 2u;
   const uint32_t b_lane = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * X3_LD + ((lane >> 3) & 1) * 8) * 2u;
 
+#pragma unroll
+  for (int s2 = 0; s2 < X3_STAGES - 1; ++s2) {
+    if (s2 * X3_BK < K) issue_b(s2, s2 * X3_BK);
+    cp_async_commit();
+  }
   load_slab(0);
+  int stage = 0;
   for (int kb = 0; kb < K; kb += X3_BK) {
-    __syncthreads();   // the previous slab has been consumed
+    cp_async_wait<X3_STAGES - 2>();   // this thread's part of the current weight slab has landed ...
+    __syncthreads();                  // ... and everyone's; the previous slab (activations and ring stage) has been consumed
     {
       uint32_t h[8], l[8];
 #pragma unroll
@@ -145,14 +168,14 @@ conv_x3_kernel(ConvParams p, const __nv_bfloat16* __restrict__ w_hi, const __nv_
       uint4* dl = reinterpret_cast<uint4*>(Al + a_pix * X3_LD + a_k0);
       dh[0] = make_uint4(h[0], h[1], h[2], h[3]); dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
       dl[0] = make_uint4(l[0], l[1], l[2], l[3]); dl[1] = make_uint4(l[4], l[5], l[6], l[7]);
-#pragma unroll
-      for (int q = 0; q < B_ELEMS / 8; ++q) {
-        *reinterpret_cast<uint4*>(Bh + b_row * X3_LD + b_k0 + 8 * q) = bh[q];
-        *reinterpret_cast<uint4*>(Bl + b_row * X3_LD + b_k0 + 8 * q) = bl[q];
-      }
+      // refill the ring stage the previous iteration multiplied from
+      const int kn = kb + (X3_STAGES - 1) * X3_BK;
+      if (kn < K) issue_b((stage + X3_STAGES - 1) % X3_STAGES, kn);
+      cp_async_commit();
     }
     __syncthreads();
     if (kb + X3_BK < K) load_slab(kb + X3_BK);   // in flight while this slab is multiplied
+    const uint32_t bh_s = bring_s + (uint32_t)(stage * 2 * B_STAGE * 2), bl_s = bh_s + (uint32_t)(B_STAGE * 2);
 #pragma unroll
     for (int ks = 0; ks < X3_BK; ks += 16) {
       uint32_t fbh[NT][2], fbl[NT][2];
@@ -180,7 +203,9 @@ conv_x3_kernel(ConvParams p, const __nv_bfloat16* __restrict__ w_hi, const __nv_
         for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[mt][nt], fah, fbh[nt][0], fbh[nt][1]);
       }
     }
+    stage = (stage + 1) % X3_STAGES;
   }
+  cp_async_wait<0>();
 
   // ---- epilogue: accumulator fragment (row = lane / 4 (+8), columns 2 * (lane % 4) + {0, 1}) ----
 #pragma unroll
@@ -213,12 +238,20 @@ bool conv_x3_supported(const ConvParams& p) {
 int launch_conv_x3(const ConvParams& p, const void* w_hi, const void* w_lo, cudaStream_t st) {
   const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(w_hi);
   const __nv_bfloat16* wl = reinterpret_cast<const __nv_bfloat16*>(w_lo);
+  constexpr int smem128 = (2 * X3_BM * X3_LD + X3_STAGES * 2 * 128 * X3_LD) * 2;
+  constexpr int smem64 = (2 * X3_BM * X3_LD + X3_STAGES * 2 * 64 * X3_LD) * 2;
+  static bool attr = false;
+  if (!attr) {
+    NIB_CUDA(cudaFuncSetAttribute(conv_x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));
+    NIB_CUDA(cudaFuncSetAttribute(conv_x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+    attr = true;
+  }
   if (p.Cout >= 128) {
     dim3 grid(ceil_div(p.M, X3_BM), ceil_div(p.Cout, 128));
-    conv_x3_kernel<128><<<grid, 256, 0, st>>>(p, wh, wl);
+    conv_x3_kernel<128><<<grid, 256, smem128, st>>>(p, wh, wl);
   } else {
     dim3 grid(ceil_div(p.M, X3_BM), ceil_div(p.Cout, 64));
-    conv_x3_kernel<64><<<grid, 256, 0, st>>>(p, wh, wl);
+    conv_x3_kernel<64><<<grid, 256, smem64, st>>>(p, wh, wl);
   }
   NIB_LAUNCH_CHECK();
   return NIB_OK;
