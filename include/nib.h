@@ -117,9 +117,16 @@ typedef struct nib_net nib_net;
 enum nib_precision {
   NIB_PREC_FP32 = 0,  /* fp32 activations/weights, SIMT kernels: the 1e-4 parity mode         */
   NIB_PREC_BF16 = 1,  /* bf16 activations/weights, fp32 accumulate, tcgen05 implicit GEMM     */
-  NIB_PREC_X3 = 2     /* fp32 activations; convs with Cin % 16 == 0 multiply split-bf16 operands
+  NIB_PREC_X3 = 2,    /* fp32 activations; convs with Cin % 16 == 0 multiply split-bf16 operands
                          (hi*hi + lo*hi + hi*lo) on the tensor cores with fp32 accumulate, ~1e-5 of
                          the fp32 mode at several times its rate: the tie policy's re-score net  */
+  NIB_PREC_SPLIT = 3  /* the same split arithmetic on the tcgen05 pair kernel: body tensors hold each value as
+                         two bf16 halves in the channel dimension ([hi(C) | lo(C)]), weights are
+                         [Wh | Wh | Wl] along K, the epilogue stores both halves of the fp32 result.
+                         Buffers are split by default; stems / pooled features live in fp32 buffers
+                         (nib_net_add_buffer_f32) joined to the body by nib_net_add_convert.  Convs on
+                         split tensors need Cin % 64 == 0 and Cout % 64 == 0 (ResNet bottleneck / basic
+                         blocks); others: NIB_PREC_X3                                             */
 };
 
 /* A network is a flat list of ops over numbered activation buffers (NHWC, per-image geometry
@@ -130,6 +137,11 @@ int nib_net_destroy(nib_net* net);
 
 /* returns buffer id >= 0.  pad = zero halo kept around H and W (0 for all but the stem input) */
 int nib_net_add_buffer(nib_net* net, int H, int W, int C, int pad);
+
+/* NIB_PREC_X3 / NIB_PREC_SPLIT / NIB_PREC_FP32 networks: an fp32 buffer whatever the network's default kind. */
+int nib_net_add_buffer_f32(nib_net* net, int H, int W, int C, int pad);
+/* NIB_PREC_SPLIT networks: out <- in across the fp32 / split boundary (same H, W, C; one side fp32, the other split). */
+int nib_net_add_convert(nib_net* net, int in_buf, int out_buf);
 
 enum nib_conv_flags {
   NIB_CONV_RELU = 1,         /* ReLU after bias (+residual)                                    */

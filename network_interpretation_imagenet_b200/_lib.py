@@ -17,7 +17,7 @@ ABI_VERSION = 2
 MASK_KEEP_MUL, MASK_REMOVE_MINMAX = 0, 1
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
-PREC_FP32, PREC_BF16, PREC_X3 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_X3, PREC_SPLIT = 0, 1, 2, 3
 CONV_RELU, CONV_PRE_BNRELU = 1, 2
 POOL_MAX, POOL_AVG = 0, 1
 IN_NCHW_F32, IN_NATIVE = 0, 1
@@ -63,6 +63,8 @@ _PROTOTYPES = {
     "nib_net_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "nib_net_destroy": (_i, [_vp]),
     "nib_net_add_buffer": (_i, [_vp, _i, _i, _i, _i]),
+    "nib_net_add_buffer_f32": (_i, [_vp, _i, _i, _i, _i]),
+    "nib_net_add_convert": (_i, [_vp, _i, _i]),
     "nib_net_add_conv": (_i, [_vp, C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "nib_net_add_pool": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "nib_net_add_fc": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -60,15 +60,20 @@ class _Builder:
         self.shapes: dict[int, tuple[int, int, int]] = {}
         self.free: dict[tuple[int, int, int], list[int]] = {}
 
-    def buffer(self, H, W, Cc, pad=0, pooled=True) -> int:
-        key = (H, W, Cc)
+    def buffer(self, H, W, Cc, pad=0, pooled=True, f32=False) -> int:
+        """f32: an fp32 buffer in a network whose default buffer kind is not fp32 (NIB_PREC_SPLIT: stem, pooled features)."""
+        key = (H, W, Cc, bool(f32))
         if pooled and pad == 0 and self.free.get(key):
             return self.free[key].pop()
-        b = self.lib.nib_net_add_buffer(self.h, H, W, Cc, pad)
+        b = (self.lib.nib_net_add_buffer_f32 if f32 else self.lib.nib_net_add_buffer)(self.h, H, W, Cc, pad)
         if b < 0:
             _lib.check(b, "nib_net_add_buffer")
         self.shapes[b] = key
         return b
+
+    def convert(self, in_buf: int, out_buf: int):
+        """fp32 <-> split bf16 boundary of a NIB_PREC_SPLIT network."""
+        _lib.check(self.lib.nib_net_add_convert(self.h, in_buf, out_buf), "nib_net_add_convert")
 
     def release(self, b: int):
         self.free.setdefault(self.shapes[b], []).append(b)
@@ -156,10 +161,13 @@ class Classifier:
 
     @staticmethod
     def _from_torch_one(module: nn.Module, input_hw, precision: str, max_batch: int) -> "Classifier":
-        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "x3": _lib.PREC_X3}[precision]
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "x3": _lib.PREC_X3, "split": _lib.PREC_SPLIT}[precision]
         m = module.module if isinstance(module, nn.DataParallel) else module  # cifar :75 wraps in DataParallel
         if hasattr(m, "layer4") and hasattr(m, "fc") and hasattr(m, "maxpool"):
             return _lower_tv_resnet(m, input_hw or (224, 224), prec, precision, max_batch)
+        if precision == "split":
+            raise TypeError("precision 'split' (split-bf16 tensors on the tcgen05 pair kernel) is lowered for torchvision "
+                            "ResNets only (every body conv needs Cin % 64 == 0 and Cout % 64 == 0); use 'x3' for this network")
         if hasattr(m, "layer3") and hasattr(m, "fc") and not hasattr(m, "layer4"):
             return _lower_resnet_cifar(m, input_hw or (32, 32), prec, precision, max_batch)
         if hasattr(m, "conv6") and hasattr(m, "fc1"):
@@ -280,18 +288,24 @@ def _lower_tv_resnet(m, hw, prec, precision, max_batch):
     # is one contiguous 128 B window (conv_tc.cu tc_conv_is_stem)
     # 4-channel pixels (8 B) inside a 3-pixel zero halo when the image has <= 3 channels: the stem's TMA box then covers
     # two filter rows per K block (conv_tc.cu tc_conv_is_stem4); 8-channel pixels otherwise
+    split = precision == "split"   # stem and pooled features in fp32 buffers, the body's tensors as bf16 [hi | lo] halves
     x_in = (b.buffer(H, W, 4 if cin <= 4 else 8, pad=3, pooled=False) if stem_tc
-            else b.buffer(H, W, _in_cpad(cin), pooled=False))
+            else b.buffer(H, W, _in_cpad(cin), pooled=False, f32=split))
     Hc, Wc = _out_hw(H, c1.kernel_size[0], c1.stride[0], c1.padding[0]), _out_hw(W, c1.kernel_size[0], c1.stride[0], c1.padding[0])
-    t = b.buffer(Hc, Wc, c1.out_channels)
+    t = b.buffer(Hc, Wc, c1.out_channels, f32=split)
     w, bias = fold_bn(c1.weight, c1.bias, m.bn1)
     b.conv(x_in, cin, t, c1.out_channels, w, bias, c1.kernel_size[0], c1.stride[0], c1.padding[0], relu=True)
     mp = m.maxpool
     k, s, p = mp.kernel_size, mp.stride, mp.padding
     Hp, Wp = _out_hw(Hc, k, s, p), _out_hw(Wc, k, s, p)
-    x = b.buffer(Hp, Wp, c1.out_channels)
+    x = b.buffer(Hp, Wp, c1.out_channels, f32=split)
     b.pool(_lib.POOL_MAX, t, c1.out_channels, x, k, s, p)
     b.release(t)
+    if split:
+        xs = b.buffer(Hp, Wp, c1.out_channels)
+        b.convert(x, xs)
+        b.release(x)
+        x = xs
     Cx, Hx, Wx = c1.out_channels, Hp, Wp
     for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
         for blk in layer:
@@ -327,7 +341,11 @@ def _lower_tv_resnet(m, hw, prec, precision, max_batch):
                 b.release(idn)
             b.release(x)
             x, Cx, Hx, Wx = cur, Cc, Hh, Ww
-    feat = b.buffer(1, 1, Cx)
+    if split:
+        xf = b.buffer(Hx, Wx, Cx, f32=True)
+        b.convert(x, xf)
+        x = xf
+    feat = b.buffer(1, 1, Cx, f32=split)
     assert Hx == Wx, "global average pool expects a square map"
     b.pool(_lib.POOL_AVG, x, Cx, feat, Hx, Hx, 0)   # AdaptiveAvgPool2d((1,1))
     b.fc(feat, Cx, m.fc.out_features, m.fc.weight, m.fc.bias)

@@ -488,4 +488,53 @@ int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int 
   return NIB_OK;
 }
 
+// ---- fp32 <-> split bf16 -------------------------------------------------------------------------
+// Boundaries of a NIB_PREC_SPLIT network (conv_tc.cu split mode): the stem and the pooled features are fp32, the body's
+// tensors carry each value as two bf16 halves in the channel dimension.  4 channels per thread.
+__global__ void __launch_bounds__(256)
+split_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long M, int C) {
+  const int g = C >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * g) return;
+  const long long m = idx / g;
+  const int c = (int)(idx - m * g) << 2;
+  const float4 v = *reinterpret_cast<const float4*>(x + m * C + c);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __float2bfloat16_rn(f[j]);
+    lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+  }
+  *reinterpret_cast<uint2*>(y + m * 2 * C + c) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(y + m * 2 * C + C + c) = *reinterpret_cast<const uint2*>(lo);
+}
+__global__ void __launch_bounds__(256)
+split_merge_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long M, int C) {
+  const int g = C >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * g) return;
+  const long long m = idx / g;
+  const int c = (int)(idx - m * g) << 2;
+  const uint2 h = *reinterpret_cast<const uint2*>(x + m * 2 * C + c), l = *reinterpret_cast<const uint2*>(x + m * 2 * C + C + c);
+  const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+  const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+  float4 o;
+  o.x = __bfloat162float(hb[0]) + __bfloat162float(lb[0]); o.y = __bfloat162float(hb[1]) + __bfloat162float(lb[1]);
+  o.z = __bfloat162float(hb[2]) + __bfloat162float(lb[2]); o.w = __bfloat162float(hb[3]) + __bfloat162float(lb[3]);
+  *reinterpret_cast<float4*>(y + m * C + c) = o;
+}
+int launch_split_convert(const void* in, void* out, long long M, int C, bool to_split, const int* dyn_n, cudaStream_t st) {
+  (void)dyn_n;   // a handful of extra rows cost less than reading the count
+  NIB_REQUIRE(C % 4 == 0, "split convert: C = %d is not a multiple of 4", C);
+  const long long total = M * (C >> 2);
+  const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
+  if (to_split)
+    split_pack_kernel<<<blocks, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, M, C);
+  else
+    split_merge_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, M, C);
+  NIB_LAUNCH_CHECK();
+  return NIB_OK;
+}
+
 }  // namespace nib

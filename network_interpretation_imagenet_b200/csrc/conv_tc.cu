@@ -60,6 +60,13 @@ struct TcKernelParams {
   int m_tiles;      // ceil(M / tile_rows)
   unsigned int* err_flag;
   unsigned long long* dbg;   // NIB_TC_DBG=1: per-CTA role timers (cycles), 16 slots per CTA; null in production
+  // split-bf16 mode of the pair kernel (NIB_PREC_SPLIT): activations are [hi | lo] channel halves, the K loop walks
+  // hi, lo, hi of every tap against weights [Wh | Wh | Wl]; the epilogue emits both halves of the fp32 result
+  int a_wrap;                // 64-channel blocks after which the A channel index wraps back to the hi half (2 * Cin / 64)
+  int lo_off_out;            // channel offset of the lo half in the output tensor
+  int lo_off_res;            // ... and in the residual tensor
+  const int* dyn_n;          // split mode: optional device-side live image count (the tie policy's re-score batch); tiles
+                             // beyond live * P * Q rows are not computed
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -411,7 +418,7 @@ static constexpr int TC3_THREADS = 64 + 256;
 // once per CTA and stays resident; the ring then carries activation tiles only, which halves the TMA instructions
 // the producer has to issue per K block (the issue rate, not the bytes, bounds these layers).
 static constexpr int TC3_BRES_KBLOCKS = 9;
-template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false, bool SPLIT = false>
 struct Tc3Smem {
   static constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
   static constexpr int BH_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;   // this CTA's half of the weight tile
@@ -424,7 +431,8 @@ struct Tc3Smem {
   static constexpr int UNITS = CW / 64;                              // 64-channel boxes per warpgroup per tile
   static constexpr int BOX_BYTES = TC_BLOCK_M * 128;
   static constexpr int RSETS = HAS_RES ? (BLOCK_N == 256 ? 1 : 2) : 1;
-  static constexpr int NBUF = HAS_RES ? RSETS * NBOX : 2;            // residual/output boxes, or 8 x 4 KB per-warp staging
+  static constexpr int RBOX = SPLIT ? 2 * NBOX : NBOX;               // boxes of one residual set (split mode: hi boxes, then lo boxes)
+  static constexpr int NBUF = HAS_RES ? RSETS * RBOX : 2;            // residual/output boxes, or 8 x 4 KB per-warp staging
   static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BOX_OFFSET = BRES_OFFSET + BRES_BYTES;
   static constexpr int BIAS_OFFSET = BOX_OFFSET + NBUF * BOX_BYTES;   // [warpgroup][2][CW] floats: the tile's folded-BN bias
@@ -559,12 +567,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_pair() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES>
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutTail,
                 const __grid_constant__ CUtensorMap tmRes, const TcKernelParams p) {
-  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
+  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES, SPLIT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) {
@@ -588,7 +596,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const int m_pairs = (p.m_tiles + 1) >> 1;
+  int m_tiles_live = p.m_tiles;
+  if (SPLIT && p.dyn_n != nullptr) {   // written many launches ago (score.cu tie_compact_kernel): safe before griddepcontrol.wait
+    const long long live = (long long)max(*p.dyn_n, 0) * p.P * p.Q;
+    const int t = (int)((live + p.tile_rows - 1) / p.tile_rows);
+    if (t < m_tiles_live) m_tiles_live = t;
+  }
+  const int m_pairs = (m_tiles_live + 1) >> 1;
   const int total_tiles = m_pairs * p.n_tiles;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   // role timers (debug builds of a launch only: p.dbg != null)
@@ -656,11 +670,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
     // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
     // busy epilogue never stalls the operand ring
-    int pend_b = SM::NBOX, pend_set = 0, pend_m0 = 0, pend_n0 = 0;
+    int pend_b = SM::RBOX, pend_set = 0, pend_m0 = 0, pend_n0 = 0;
     uint32_t pend_par = 0;
     auto issue_pending = [&](bool block) {
-      while (pend_b < SM::NBOX) {
-        const int buf = pend_set * SM::NBOX + pend_b;
+      while (pend_b < SM::RBOX) {
+        const int buf = pend_set * SM::RBOX + pend_b;
         if (block) {
           TC3_TIMED(1, mbar_wait(box_free_bar(buf), pend_par ^ 1u, p.err_flag, 4));
         } else {
@@ -669,7 +683,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (elect_one()) {
           mbar_arrive_expect_tx(res_full_bar(buf), (uint32_t)SM::BOX_BYTES);
-          tma_load_2d(box_addr(buf), &tmRes, res_full_bar(buf), p.res_coff + pend_n0 + 64 * pend_b, pend_m0);
+          const int rc = SPLIT ? p.res_coff + pend_n0 + 64 * (pend_b % SM::NBOX) + (pend_b >= SM::NBOX ? p.lo_off_res : 0)
+                               : p.res_coff + pend_n0 + 64 * pend_b;
+          tma_load_2d(box_addr(buf), &tmRes, res_full_bar(buf), rc, pend_m0);
         }
         __syncwarp();
         ++pend_b;
@@ -718,7 +734,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t a_dst = smem_base + stage * SM::STAGE_BYTES;
           const uint32_t lbar = lbar0 + 8u * stage;
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-          const int c0 = cb * TC_BLOCK_K + p.in_coff;
+          const int ca = SPLIT ? (cb >= p.a_wrap ? cb - p.a_wrap : cb) : cb;   // split mode: hi, lo, hi again
+          const int c0 = ca * TC_BLOCK_K + p.in_coff;
           if (p.im2col == 1) {
             tma2_load_im2col_4d(a_dst, &tmA, lbar, c0, w0, h0, img, (uint16_t)tap_s, (uint16_t)tap_r);
           } else if (p.im2col == 2) {
@@ -848,11 +865,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
       for (int u = 0; u < SM::UNITS; ++u) {
         const int b = SM::SPLIT_COLS ? g * SM::UNITS + u : 0;                   // output box (64 channels) of the tile
-        const int buf = set * SM::NBOX + b;                                    // residual/output box (HAS_RES)
+        const int buf = set * SM::RBOX + b;                                    // residual/output box (HAS_RES)
         const uint32_t slab = HAS_RES ? box_addr(buf) + (uint32_t)(quarter * 4096)
                                       : smem_base + SM::BOX_OFFSET + (uint32_t)(ew * 4096);
         const uint32_t obase = slab + (uint32_t)lane * 128u;
         if (HAS_RES) TC3_TIMED(1, mbar_wait(res_full_bar(buf), rpar, p.err_flag, 6));
+        if (HAS_RES && SPLIT) TC3_TIMED(1, mbar_wait(res_full_bar(buf + SM::NBOX), rpar, p.err_flag, 6));
         uint32_t v[64];
         __syncwarp();
         tmem_ld_32x32b_x64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BLOCK_N + b * 64), v);
@@ -861,6 +879,75 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(ab ? lead_empty1 : lead_empty0);
+        }
+        if constexpr (SPLIT) {
+          // fp32 result -> (hi, lo) bf16 halves.  hi goes to the hi box / the private slab, lo to the lo box / the same slab
+          // once the hi store has read it; the residual is the sum of its own two halves, added in fp32.
+          const int buf_lo = buf + SM::NBOX;
+          const uint32_t slab_lo = HAS_RES ? box_addr(buf_lo) + (uint32_t)(quarter * 4096) : slab;
+          const uint32_t obase_lo = slab_lo + (uint32_t)lane * 128u;
+          const uint32_t bsrc = bias_s + (uint32_t)(u * 64 * 4);
+          uint32_t lo[32];
+          if (!HAS_RES) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[c * 8 + j]);
+            if (has_bias) {
+              const uint4 b0 = lds_v4(bsrc + (uint32_t)(c * 32)), b1 = lds_v4(bsrc + (uint32_t)(c * 32 + 16));
+              x[0] += __uint_as_float(b0.x); x[1] += __uint_as_float(b0.y); x[2] += __uint_as_float(b0.z); x[3] += __uint_as_float(b0.w);
+              x[4] += __uint_as_float(b1.x); x[5] += __uint_as_float(b1.y); x[6] += __uint_as_float(b1.z); x[7] += __uint_as_float(b1.w);
+            }
+            const uint32_t swz = (((uint32_t)c) ^ sw) << 4;
+            if (HAS_RES) {
+              const uint4 rh = lds_v4(obase + swz), rl = lds_v4(obase_lo + swz);
+              const uint32_t h4[4] = {rh.x, rh.y, rh.z, rh.w}, l4[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                x[2 * j] += __uint_as_float(h4[j] << 16) + __uint_as_float(l4[j] << 16);
+                x[2 * j + 1] += __uint_as_float(h4[j] & 0xFFFF0000u) + __uint_as_float(l4[j] & 0xFFFF0000u);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+            }
+            uint32_t h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(x[2 * j + 1]), "f"(x[2 * j]));
+              const float r0 = x[2 * j] - __uint_as_float(h[j] << 16), r1 = x[2 * j + 1] - __uint_as_float(h[j] & 0xFFFF0000u);
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo[c * 4 + j]) : "f"(r1), "f"(r0));
+            }
+            sts_v4(obase + swz, make_uint4(h[0], h[1], h[2], h[3]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, slab, p.out_coff + n0 + b * 64, m0 + quarter * 32);
+            bulk_commit();
+            if (!HAS_RES) bulk_wait_read<0>();     // the slab is about to be overwritten with the lo half
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts_v4(obase_lo + ((((uint32_t)c) ^ sw) << 4), make_uint4(lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, slab_lo, p.out_coff + p.lo_off_out + n0 + b * 64, m0 + quarter * 32);
+            bulk_commit();
+            if (HAS_RES) {
+              bulk_wait_read<0>();
+              mbar_arrive(box_free_bar(buf));
+              mbar_arrive(box_free_bar(buf_lo));
+            }
+          }
+          continue;
         }
         uint32_t o[32];
         const uint32_t bsrc = bias_s + (uint32_t)(u * 64 * 4);
@@ -1369,6 +1456,7 @@ struct TcConvPlan {
   CUtensorMap tmBh;   // pair kernel: weight map with a BLOCK_N/2-row box (each CTA of the pair loads half of the tile)
   CUtensorMap tmOut32, tmOutTail;   // pair kernel: per-warp 32-row output boxes (+ the short last box of a 112-row stem tile)
   int v3;             // 1: the CTA-pair kernel serves this layer; 0: the one-CTA kernel (Cout = 32, NIB_TC_V1)
+  int split;          // split-bf16 tensors: K = 3 x Cin per tap, both halves of the result are stored
   int block_n, stages;
   int im2col;
   int tile_rows;
@@ -1421,6 +1509,15 @@ bool tc_conv_is_stem4(const ConvParams& p) {
 }
 
 bool tc_conv_supported(const ConvParams& p) {
+  if (p.split) {
+    // hi / lo halves must be adjacent (the K loop wraps from the lo blocks back to the hi blocks), 64-channel granularity
+    if (p.Cin % TC_BLOCK_K != 0 || p.Cout % 64 != 0 || p.in_coff != 0 || p.out_coff != 0 || p.in_lo_off != p.Cin) return false;
+    if (p.in_cstride != 2 * p.Cin || p.out_cstride < p.out_lo_off + p.Cout || p.out_lo_off % 64 != 0) return false;
+    if (p.in_halo != 0 || p.out_halo != 0 || p.pre_scale != nullptr || p.R != p.S || p.pad > 127 || p.R > 16) return false;
+    if (p.res != nullptr && (p.res_C != p.Cout || p.res_coff != 0 || p.res_lo_off % 64 != 0 || p.res_cstride < p.res_lo_off + p.Cout))
+      return false;
+    return true;
+  }
   if (tc_conv_is_stem(p) || tc_conv_is_stem4(p)) return true;
   if (p.Cin % TC_BLOCK_K != 0) return false;
   if (p.in_cstride % 8 != 0 || p.in_coff % 8 != 0) return false;   // 16 B TMA alignment
@@ -1551,10 +1648,11 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
     *out = plan;
     return NIB_OK;
   }
-  plan->cblocks = p.Cin / TC_BLOCK_K;
+  plan->split = p.split;
+  plan->cblocks = (p.split ? 3 : 1) * p.Cin / TC_BLOCK_K;
   plan->num_k_blocks = p.R * p.S * plan->cblocks;
   plan->im2col = !(p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0);
-  const int K = p.R * p.S * p.Cin;
+  const int K = p.R * p.S * p.Cin * (p.split ? 3 : 1);
   // B: weights [Cout][K]
   rc = encode_2d_bf16(&plan->tmB, p.w, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, TC_BLOCK_K, plan->block_n);
   if (rc != NIB_OK) { delete plan; return rc; }
@@ -1613,6 +1711,7 @@ bool tc_fuse_supported(const ConvParams& c, const ConvParams& a) {
   if (e != nullptr && atoi(e) == 0) return false;
   static const bool v1_only = getenv("NIB_TC_V1") != nullptr;
   if (v1_only) return false;
+  if (c.split || a.split) return false;   // the fused kernel's staging box is a plain bf16 operand
   if (!compact_1x1(c) || !compact_1x1(a)) return false;
   if (c.res == nullptr || c.res_C != c.Cout || c.res_cstride != c.Cout || c.res_coff != 0) return false;
   if (c.Cin % TC_BLOCK_K != 0 || c.Cin > 256 || c.Cout % 256 != 0 || c.Cout > 1024) return false;
@@ -1755,13 +1854,13 @@ static int launch_tc(const TcConvPlan* plan, const TcKernelParams& kp, int tiles
   return NIB_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false>
+template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES = false, bool SPLIT = false>
 static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStream_t st) {
-  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES>;
+  using SM = Tc3Smem<BLOCK_N, STAGES, HAS_RES, BRES, SPLIT>;
   static_assert(SM::TOTAL <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static bool attr_set = false;
   if (!attr_set) {
-    NIB_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES, BRES>,
+    NIB_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES, BRES, SPLIT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
@@ -1784,12 +1883,20 @@ static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl && cap == cudaStreamCaptureStatusNone && kp.dbg == nullptr) ? 1 : 0;
-  NIB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES, BRES>, plan->tmA, plan->tmBh, plan->tmOut32,
+  NIB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BLOCK_N, STAGES, HAS_RES, BRES, SPLIT>, plan->tmA, plan->tmBh, plan->tmOut32,
                               plan->tmOutTail, plan->tmRes, kp));
   return NIB_OK;
 }
 
 static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int tiles, cudaStream_t st) {
+  if (plan->split) {
+    // split-bf16 tensors: twice the residual / staging boxes, so shallower operand rings where a residual is added
+    const bool res = kp.res != nullptr;
+    if (!plan->v3 || kp.out_f32) { set_error("tc_dispatch: split mode needs the CTA-pair kernel"); return NIB_EINVAL; }
+    if (plan->block_n == 256) return res ? launch_tc3<256, 3, true, false, true>(plan, kp, st) : launch_tc3<256, 6, false, false, true>(plan, kp, st);
+    if (plan->block_n == 128) return res ? launch_tc3<128, 4, true, false, true>(plan, kp, st) : launch_tc3<128, 8, false, false, true>(plan, kp, st);
+    return res ? launch_tc3<64, 8, true, false, true>(plan, kp, st) : launch_tc3<64, 9, false, false, true>(plan, kp, st);
+  }
   if (plan->v3 && !kp.out_f32) {
     // CTA-pair kernel; stage counts fill the 227 KB of each SM (ring + output/residual boxes)
     const bool res = kp.res != nullptr;
@@ -1890,6 +1997,10 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.tile_rows = plan->tile_rows;
   kp.a_bytes = plan->tile_rows * TC_BLOCK_K * 2;
   kp.m_tiles = ceil_div(p.M, plan->tile_rows);
+  kp.a_wrap = plan->split ? 2 * p.Cin / TC_BLOCK_K : plan->cblocks;
+  kp.lo_off_out = p.out_lo_off;
+  kp.lo_off_res = p.res_lo_off;
+  kp.dyn_n = plan->split ? p.dyn_n : nullptr;
   const int tiles = kp.m_tiles * kp.n_tiles;
   static const bool dbg = getenv("NIB_TC_DBG") != nullptr;
   if (dbg && plan->v3) return tc_launch_debug(plan, kp, p, tiles, st);

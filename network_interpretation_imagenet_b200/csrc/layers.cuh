@@ -21,6 +21,11 @@ struct ConvParams {
   int relu;
   const int* dyn_n;     // optional device int: live image count (<= M / (P*Q)); rows of the images beyond it are skipped
                         // by the CUDA-core kernels (the fp32 tie re-score runs on a device-side count, score.cu)
+  // split-bf16 tensors (NIB_PREC_SPLIT, conv_tc.cu): Cin / Cout / res_C stay LOGICAL channel counts, the *_cstride values
+  // are the physical ones (2 x logical), `w` is the [Cout][R*S][3*Cin] arrangement [Wh | Wh | Wl]; the lo half of each
+  // tensor starts *_lo_off channels after its hi half
+  int split;
+  int in_lo_off, out_lo_off, res_lo_off;
 };
 
 struct PoolParams {
@@ -47,6 +52,8 @@ int launch_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* out, i
                         cudaStream_t st);
 int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int halo, bool bf16, float* out,
                         cudaStream_t st);
+// fp32 [M][C] <-> split bf16 [M][hi(C) | lo(C)], x = hi + lo with hi = bf16(x), lo = bf16(x - hi)   (NIB_PREC_SPLIT)
+int launch_split_convert(const void* in, void* out, long long M, int C, bool to_split, const int* dyn_n, cudaStream_t st);
 int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo);
 
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ---------------------------------------------

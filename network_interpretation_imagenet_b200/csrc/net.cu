@@ -13,14 +13,19 @@
 
 using namespace nib;
 
+enum BufKind { BUF_F32 = 0, BUF_BF16 = 1, BUF_SPLIT = 2 };   // BUF_SPLIT: bf16 [hi(C) | lo(C)] per pixel, x = hi + lo
+
 struct NetBuffer {
-  int H, W, C, pad;
+  int H, W, C, pad;      // C = logical channels
+  int kind;              // BufKind
   void* ptr;
-  size_t elems_per_image;
+  size_t elems_per_image;   // physical elements (2 * C per pixel for BUF_SPLIT)
+  int phys_c() const { return kind == BUF_SPLIT ? 2 * C : C; }
+  size_t esize() const { return kind == BUF_F32 ? 4 : 2; }
 };
 
 struct NetOp {
-  int kind;  // 0 conv, 1 pool, 2 fc
+  int kind;  // 0 conv, 1 pool, 2 fc, 3 convert (fp32 <-> split)
   nib_conv_desc cd;
   void* d_w;          // conv: KRSC in net dtype; fc: fp32 [Cout][Cin]
   void* d_w_alt;      // 7x7/2 stem in bf16 nets: [Cout][7][8][8] packing for the tcgen05 row-window path
@@ -50,6 +55,7 @@ struct nib_net {
   int max_batch;
   bool bf16;
   bool x3;                    // fp32 activations, split-bf16 tensor-core products for the convs that qualify
+  bool split;                 // NIB_PREC_SPLIT: body tensors are BUF_SPLIT, convs run on the tcgen05 pair kernel in split mode
   std::vector<NetBuffer> bufs;
   std::vector<NetOp> ops;
   void* pack_scratch;        // [max_batch * H * W][pack_cin] bf16: relu(bn(x)) of the conv being run (largest such layer)
@@ -93,13 +99,14 @@ extern "C" {
 int nib_net_create(int precision, int max_batch, nib_net** out) {
   NIB_DEVICE_OR_FAIL();
   NIB_REQUIRE(out != nullptr, "nib_net_create: null out");
-  NIB_REQUIRE(precision == NIB_PREC_FP32 || precision == NIB_PREC_BF16 || precision == NIB_PREC_X3,
+  NIB_REQUIRE(precision == NIB_PREC_FP32 || precision == NIB_PREC_BF16 || precision == NIB_PREC_X3 || precision == NIB_PREC_SPLIT,
               "nib_net_create: bad precision %d", precision);
   NIB_REQUIRE(max_batch > 0, "nib_net_create: max_batch must be > 0");
   nib_net* n = new nib_net();
   n->precision = precision;
   n->bf16 = precision == NIB_PREC_BF16;
   n->x3 = precision == NIB_PREC_X3;
+  n->split = precision == NIB_PREC_SPLIT;
   n->max_batch = max_batch;
   n->input_buf = -1;
   n->pack_scratch = nullptr;
@@ -138,19 +145,49 @@ int nib_net_destroy(nib_net* net) {
   return NIB_OK;
 }
 
-int nib_net_add_buffer(nib_net* net, int H, int W, int C, int pad) {
+static int add_buffer_kind(nib_net* net, int H, int W, int C, int pad, int kind) {
   NIB_REQUIRE(net && !net->finalized, "nib_net_add_buffer: bad handle/state");
   NIB_REQUIRE(H > 0 && W > 0 && C > 0 && pad >= 0, "nib_net_add_buffer: bad geometry");
   NetBuffer b;
   b.H = H; b.W = W; b.C = C; b.pad = pad;
-  b.elems_per_image = (size_t)(H + 2 * pad) * (W + 2 * pad) * C;
-  size_t bytes = b.elems_per_image * net->max_batch * elem_size(net);
+  b.kind = kind;
+  b.elems_per_image = (size_t)(H + 2 * pad) * (W + 2 * pad) * b.phys_c();
+  size_t bytes = b.elems_per_image * net->max_batch * b.esize();
   // one extra tile row block of slack: TMA boxes never read past the tensor-map extent, but SIMT
   // vector loads on the last pixel may touch up to 16 B beyond the last channel group.
   NIB_CUDA(cudaMalloc(&b.ptr, bytes + 256));
   NIB_CUDA(cudaMemset(b.ptr, 0, bytes + 256));
   net->bufs.push_back(b);
   return (int)net->bufs.size() - 1;
+}
+
+int nib_net_add_buffer(nib_net* net, int H, int W, int C, int pad) {
+  NIB_REQUIRE(net != nullptr, "nib_net_add_buffer: null handle");
+  return add_buffer_kind(net, H, W, C, pad, net->bf16 ? BUF_BF16 : net->split ? BUF_SPLIT : BUF_F32);
+}
+
+int nib_net_add_buffer_f32(nib_net* net, int H, int W, int C, int pad) {
+  NIB_REQUIRE(net != nullptr, "nib_net_add_buffer_f32: null handle");
+  NIB_REQUIRE(!net->bf16, "nib_net_add_buffer_f32: bf16 networks have bf16 buffers only");
+  return add_buffer_kind(net, H, W, C, pad, BUF_F32);
+}
+
+int nib_net_add_convert(nib_net* net, int in_buf, int out_buf) {
+  NIB_REQUIRE(net && !net->finalized && net->split, "nib_net_add_convert: needs an unfinalized NIB_PREC_SPLIT network");
+  const int nb = (int)net->bufs.size();
+  NIB_REQUIRE(in_buf >= 0 && in_buf < nb && out_buf >= 0 && out_buf < nb, "nib_net_add_convert: bad buffer id");
+  const NetBuffer& bi = net->bufs[in_buf];
+  const NetBuffer& bo = net->bufs[out_buf];
+  NIB_REQUIRE(bi.H == bo.H && bi.W == bo.W && bi.C == bo.C && bi.pad == 0 && bo.pad == 0, "nib_net_add_convert: geometry mismatch");
+  NIB_REQUIRE((bi.kind == BUF_F32 && bo.kind == BUF_SPLIT) || (bi.kind == BUF_SPLIT && bo.kind == BUF_F32),
+              "nib_net_add_convert: one side must be fp32, the other split");
+  NetOp op;
+  memset(&op, 0, sizeof(op));
+  op.kind = 3;
+  op.in_buf = in_buf;
+  op.out_buf = out_buf;
+  net->ops.push_back(op);
+  return NIB_OK;
 }
 
 int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight, const float* h_bias,
@@ -179,6 +216,9 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
   memset(&op, 0, sizeof(op));
   op.kind = 0;
   op.cd = *d;
+  NIB_REQUIRE(bi.kind == bo.kind, "nib_net_add_conv: input and output buffers must have the same kind (use nib_net_add_convert)");
+  if (d->res_buf >= 0) NIB_REQUIRE(net->bufs[d->res_buf].kind == bo.kind, "nib_net_add_conv: residual buffer kind mismatch");
+  const bool split_op = bi.kind == BUF_SPLIT;
   const size_t K = (size_t)d->R * d->S * d->Cin;
   const size_t nel = K * d->Cout;
   // [Cout][Cin][R][S] -> [Cout][R][S][Cin]
@@ -189,7 +229,27 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
         for (int s = 0; s < d->S; ++s)
           krsc[(((size_t)co * d->R + r) * d->S + s) * d->Cin + c] =
               h_weight[(((size_t)co * d->Cin + c) * d->R + r) * d->S + s];
-  if (net->bf16) {
+  if (split_op) {
+    // [Cout][tap][Wh(Cin) | Wh(Cin) | Wl(Cin)]: against activations walked as hi, lo, hi (conv_tc.cu split mode)
+    const size_t taps = (size_t)d->R * d->S;
+    std::vector<uint16_t> hb(nel * 3);
+    for (int co = 0; co < d->Cout; ++co)
+      for (size_t t = 0; t < taps; ++t)
+        for (int c = 0; c < d->Cin; ++c) {
+          const float w = krsc[((size_t)co * taps + t) * d->Cin + c];
+          const uint16_t hi = f32_to_bf16_rn(w);
+          uint32_t u = (uint32_t)hi << 16;
+          float hf;
+          memcpy(&hf, &u, 4);
+          const uint16_t lo = f32_to_bf16_rn(w - hf);
+          const size_t base = ((size_t)co * taps + t) * 3 * d->Cin;
+          hb[base + c] = hi;
+          hb[base + d->Cin + c] = hi;
+          hb[base + 2 * (size_t)d->Cin + c] = lo;
+        }
+    NIB_CUDA(cudaMalloc(&op.d_w, hb.size() * 2 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  } else if (net->bf16) {
     std::vector<uint16_t> hb(nel);
     for (size_t i = 0; i < nel; ++i) hb[i] = f32_to_bf16_rn(krsc[i]);
     NIB_CUDA(cudaMalloc(&op.d_w, nel * 2 + 256));
@@ -271,6 +331,7 @@ int nib_net_add_pool(nib_net* net, int kind, int in_buf, int in_coff, int C, int
   const NetBuffer& bi = net->bufs[in_buf];
   const NetBuffer& bo = net->bufs[out_buf];
   NIB_REQUIRE(bi.pad == 0 && bo.pad == 0, "nib_net_add_pool: halo buffers unsupported");
+  NIB_REQUIRE(bi.kind == bo.kind && bi.kind != BUF_SPLIT, "nib_net_add_pool: pooling runs on fp32 or bf16 buffers (convert split tensors first)");
   NIB_REQUIRE(in_coff + C <= bi.C && out_coff + C <= bo.C, "nib_net_add_pool: channel slice out of range");
   const int P = (bi.H + 2 * pad - k) / stride + 1, Q = (bi.W + 2 * pad - k) / stride + 1;
   NIB_REQUIRE(P == bo.H && Q == bo.W, "nib_net_add_pool: output buffer is %dx%d but pool produces %dx%d", bo.H, bo.W, P, Q);
@@ -292,6 +353,7 @@ int nib_net_add_fc(nib_net* net, int in_buf, int Cin, int Cout, const float* h_w
   NIB_REQUIRE(in_buf >= 0 && in_buf < (int)net->bufs.size(), "nib_net_add_fc: bad buffer id");
   const NetBuffer& bi = net->bufs[in_buf];
   NIB_REQUIRE(bi.H == 1 && bi.W == 1 && bi.C >= Cin, "nib_net_add_fc: input must be a 1x1xC feature buffer");
+  NIB_REQUIRE(bi.kind != BUF_SPLIT, "nib_net_add_fc: the feature buffer must be fp32 or bf16");
   NetOp op;
   memset(&op, 0, sizeof(op));
   op.kind = 2;
@@ -325,13 +387,17 @@ static void fill_conv_params(const nib_net* net, const NetOp& op, int N, ConvPar
   p->out = bo.ptr;
   p->pre_scale = op.d_pre_scale;
   p->pre_shift = op.d_pre_shift;
-  p->Hin = bi.H; p->Win = bi.W; p->Cin = d.Cin; p->in_cstride = bi.C; p->in_coff = d.in_coff; p->in_halo = bi.pad;
-  p->P = bo.H; p->Q = bo.W; p->Cout = d.Cout; p->out_cstride = bo.C; p->out_coff = d.out_coff; p->out_halo = bo.pad;
+  p->Hin = bi.H; p->Win = bi.W; p->Cin = d.Cin; p->in_cstride = bi.phys_c(); p->in_coff = d.in_coff; p->in_halo = bi.pad;
+  p->P = bo.H; p->Q = bo.W; p->Cout = d.Cout; p->out_cstride = bo.phys_c(); p->out_coff = d.out_coff; p->out_halo = bo.pad;
+  p->split = bi.kind == BUF_SPLIT ? 1 : 0;
+  p->in_lo_off = bi.C;
+  p->out_lo_off = bo.C;
   p->M = N * bo.H * bo.W;
   if (d.res_buf >= 0) {
     const NetBuffer& br = net->bufs[d.res_buf];
     p->res = br.ptr;
-    p->res_cstride = br.C; p->res_coff = d.res_coff; p->res_C = d.res_C;
+    p->res_cstride = br.phys_c(); p->res_coff = d.res_coff; p->res_C = d.res_C;
+    p->res_lo_off = br.C;
   }
   p->R = d.R; p->S = d.S; p->stride = d.stride; p->pad = d.pad;
   p->relu = (d.flags & NIB_CONV_RELU) ? 1 : 0;
@@ -354,6 +420,16 @@ int nib_net_finalize(nib_net* net) {
   NIB_REQUIRE(net && !net->finalized, "nib_net_finalize: bad handle/state");
   NIB_REQUIRE(net->input_buf >= 0, "nib_net_finalize: input buffer not set");
   NIB_REQUIRE(!net->ops.empty() && net->ops.back().kind == 2, "nib_net_finalize: the last op must be the fc layer");
+  if (net->split) {
+    for (auto& op : net->ops) {
+      if (op.kind != 0 || net->bufs[op.cd.in_buf].kind != BUF_SPLIT) continue;
+      ConvParams p;
+      fill_conv_params(net, op, net->max_batch, &p);
+      NIB_REQUIRE(tc_conv_supported(p), "nib_net_finalize: a conv on split tensors needs Cin %% 64 == 0, Cout %% 64 == 0, whole-buffer channel ranges (Cin=%d Cout=%d)", p.Cin, p.Cout);
+      int rc = tc_conv_plan_create(p, net->max_batch, &op.plan);
+      if (rc != NIB_OK) return rc;
+    }
+  }
   if (net->bf16) {
     // one scratch tensor serves every packed pre-activation conv (ops run one at a time on the stream)
     for (auto& op : net->ops) {
@@ -432,7 +508,7 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
         fill_packed_conv_params(net, op, N, &p);
         rc = tc_conv_launch(op.plan, p, st);
         net->tc_launches++;
-      } else if (op.plan && net->use_tc) {
+      } else if (op.plan && (net->use_tc || net->split)) {
         rc = tc_conv_launch(op.plan, p, st);
         net->tc_launches++;
       } else if (net->x3 && op.d_w_hi && conv_x3_supported(p)) {
@@ -441,6 +517,12 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
       } else {
         rc = launch_conv_simt(p, net->bf16, st);
       }
+      net->launches++;
+      if (rc != NIB_OK) return rc;
+    } else if (op.kind == 3) {
+      const NetBuffer& bi = net->bufs[op.in_buf];
+      const NetBuffer& bo = net->bufs[op.out_buf];
+      int rc = launch_split_convert(bi.ptr, bo.ptr, (long long)N * bi.H * bi.W, bi.C, bi.kind == BUF_F32, net->dyn_n, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
     } else if (op.kind == 1) {
@@ -455,12 +537,12 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
       p.P = bo.H; p.Q = bo.W; p.out_cstride = bo.C; p.out_coff = op.out_coff;
       p.k = op.k; p.stride = op.stride; p.pad = op.pad;
       p.dyn_n = net->dyn_n;
-      int rc = launch_pool(p, net->bf16, st);
+      int rc = launch_pool(p, bi.kind == BUF_BF16, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
     } else {
       const NetBuffer& bi = net->bufs[op.fc_in];
-      int rc = launch_fc(bi.ptr, bi.C, net->bf16, (const float*)op.d_w, op.d_bias, N, op.fc_cin, op.fc_cout,
+      int rc = launch_fc(bi.ptr, bi.C, bi.kind == BUF_BF16, (const float*)op.d_w, op.d_bias, N, op.fc_cin, op.fc_cout,
                          d_logits, net->dyn_n, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
@@ -471,6 +553,7 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
 
 static int stage_input(nib_net* net, const void* d_x, int x_layout, int N, cudaStream_t st) {
   const NetBuffer& bi = net->bufs[net->input_buf];
+  NIB_REQUIRE(bi.kind != BUF_SPLIT, "nib_net_forward: the input buffer of a split network must be fp32 (nib_net_add_buffer_f32)");
   if (x_layout == NIB_IN_NCHW_F32) {
     // the reference hands an N x C x H x W fp32 tensor (imagenet :245); channels beyond the model's
     // real C are zero padding for the tensor-core path.
@@ -577,13 +660,13 @@ int nib_net_profile(nib_net* net, int N, float* h_ms, int* h_kind, double* h_flo
         g[0] = bo.H; g[1] = bo.W; g[2] = op.cd.Cin; g[3] = op.cd.Cout; g[4] = op.cd.R; g[5] = op.cd.stride;
         g[6] = op.cd.res_buf >= 0; g[7] = op.plan ? tc_conv_plan_block_n(op.plan) : 0;
       }
-    } else if (op.kind == 1) {
+    } else if (op.kind == 1 || op.kind == 3) {
       h_kind[i] = 2;
       h_flops[i] = 0.0;
       if (h_geom) {
         const NetBuffer& bo = net->bufs[op.out_buf];
         int* g = h_geom + 8 * i;
-        g[0] = bo.H; g[1] = bo.W; g[2] = op.C; g[3] = op.C; g[4] = op.k; g[5] = op.stride; g[6] = 0; g[7] = 0;
+        g[0] = bo.H; g[1] = bo.W; g[2] = bo.C; g[3] = bo.C; g[4] = op.kind == 1 ? op.k : 0; g[5] = op.kind == 1 ? op.stride : 1; g[6] = 0; g[7] = 0;
       }
     } else {
       h_kind[i] = 3;
@@ -629,7 +712,7 @@ int nib_net_buffer_info(nib_net* net, int buf, void** d_ptr, int* H, int* W, int
   if (W) *W = b.W;
   if (C) *C = b.C;
   if (pad) *pad = b.pad;
-  if (dtype) *dtype = net->bf16 ? NIB_BF16 : NIB_F32;
+  if (dtype) *dtype = b.kind == BUF_F32 ? NIB_F32 : b.kind == BUF_BF16 ? NIB_BF16 : 2 /* split: bf16 [hi | lo] */;
   return NIB_OK;
 }
 
@@ -638,7 +721,8 @@ int nib_net_read_buffer_nchw(nib_net* net, int buf, int N, float* d_out, void* s
   NIB_REQUIRE(net && buf >= 0 && buf < (int)net->bufs.size() && d_out, "nib_net_read_buffer_nchw: bad arguments");
   NIB_REQUIRE(N > 0 && N <= net->max_batch, "nib_net_read_buffer_nchw: bad N");
   const NetBuffer& b = net->bufs[buf];
-  return launch_nhwc_to_nchw(b.ptr, N, b.C, b.H, b.W, b.C, b.pad, net->bf16, d_out, (cudaStream_t)stream);
+  NIB_REQUIRE(b.kind != BUF_SPLIT, "nib_net_read_buffer_nchw: convert a split buffer to fp32 first (nib_net_add_convert)");
+  return launch_nhwc_to_nchw(b.ptr, N, b.C, b.H, b.W, b.C, b.pad, b.kind == BUF_BF16, d_out, (cudaStream_t)stream);
 }
 
 int nib_net_launch_counts(nib_net* net, long long* total, long long* tcgen05) {
@@ -650,6 +734,7 @@ int nib_net_launch_counts(nib_net* net, long long* total, long long* tcgen05) {
 
 int nib_net_set_tensor_core(nib_net* net, int enable) {
   NIB_REQUIRE(net != nullptr, "nib_net_set_tensor_core: null handle");
+  NIB_REQUIRE(enable || !net->split, "nib_net_set_tensor_core: split-bf16 tensors exist only on the tensor path");
   net->use_tc = enable != 0;
   for (auto& g : net->graphs) cudaGraphExecDestroy(g.second.exec);
   net->graphs.clear();

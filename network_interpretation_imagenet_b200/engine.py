@@ -99,8 +99,9 @@ class ScoreComm:
 
 class PerturbationEngine:
     """refine_ties: relative top-2 margin (top1 - runner-up) / max|logit| below which a bf16-scored mask is re-scored by
-    an fp32-grade copy of the classifier (`tie_precision`: "x3" = fp32 activations with split-bf16 tensor-core products,
-    within ~1e-5 of the fp32 lowering at several times its rate; "fp32" = the CUDA-core lowering itself), so that top-1
+    an fp32-grade copy of the classifier (`tie_precision`: "split" = the tcgen05 pair kernel over split-bf16 tensors,
+    torchvision ResNets only; "x3" = fp32 activations with split-bf16 mma.sync products; both within ~3e-5 of the fp32
+    lowering; "fp32" = the CUDA-core lowering itself; "auto" picks "split" where it applies, else "x3"), so that top-1
     equals the reference's on every mask outside numerical noise.
     "auto" (default) = DEFAULT_TIE_BAND for bf16 classifiers lowered from a torch module, off otherwise; None/0 = off.
     The policy runs entirely on the device (no host synchronisation): near-tie rows are compacted into a buffer of
@@ -111,7 +112,7 @@ class PerturbationEngine:
     def __init__(self, model, image, segments, target: int, mode: int = KEEP_MUL, precision: str = "bf16",
                  max_batch: int = 128, S: int | None = None, device="cuda", group=None, use_graph: bool = False,
                  refine_ties="auto", streams: int = 1, tie_capacity: int = DEFAULT_TIE_CAPACITY,
-                 tie_window: int = DEFAULT_TIE_WINDOW, tie_precision: str = "x3"):
+                 tie_window: int = DEFAULT_TIE_WINDOW, tie_precision: str = "auto"):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.target = int(target)
@@ -130,8 +131,13 @@ class PerturbationEngine:
             raise ValueError("refine_ties needs the torch module (to lower an fp32 copy), not a lowered Classifier")
         self.tie_capacity = int(tie_capacity)
         self.tie_window = max(1, int(tie_window))
-        if tie_precision not in ("x3", "fp32"):
-            raise ValueError("tie_precision must be 'x3' (split-bf16 tensor-core products, fp32 accumulate) or 'fp32' (CUDA cores)")
+        if tie_precision == "auto":
+            # torchvision ResNets (every body conv a multiple of 64 channels wide) re-score on the tcgen05 pair kernel over
+            # split-bf16 tensors; everything else on the mma.sync split-bf16 kernel over fp32 tensors
+            tie_precision = "split" if self.classifier.arch == "tv_resnet" else "x3"
+        if tie_precision not in ("split", "x3", "fp32"):
+            raise ValueError("tie_precision must be 'auto', 'split' (split-bf16 tensors, tcgen05), 'x3' (split-bf16 products on "
+                             "fp32 tensors, mma.sync) or 'fp32' (CUDA cores)")
         self.tie_precision = tie_precision
         self._fp32 = None
         self._tie = None

@@ -121,11 +121,16 @@ def test_tie_policy_is_device_side_and_bounded(bench_setup):
     # the default re-score precision (split-bf16 tensor-core products): same rows refined, scores within 1e-4 of the fp32 ones
     engx = nib.PerturbationEngine(s["model"], s["x"], s["seg"], target=0, mode=nib.KEEP_MUL, precision="bf16", max_batch=64,
                                   S=50, refine_ties=10.0, tie_capacity=16)
-    assert engx.tie_precision == "x3"
+    assert engx.tie_precision == "split"          # torchvision ResNet: the tcgen05 pair kernel over split-bf16 tensors
     outx = engx.score_masks(bits)
     assert torch.equal(outx["top1"][:16], s32["top1"])
     assert torch.allclose(outx["target_prob"][:16], s32["target_prob"], rtol=1e-4, atol=0)
     assert torch.equal(outx["target_prob"][16:], s16["target_prob"][16:])
+    engy = nib.PerturbationEngine(s["model"], s["x"], s["seg"], target=0, mode=nib.KEEP_MUL, precision="bf16", max_batch=64,
+                                  S=50, refine_ties=10.0, tie_capacity=16, tie_precision="x3")
+    outy = engy.score_masks(bits)
+    assert torch.equal(outy["top1"][:16], s32["top1"])
+    assert torch.allclose(outy["target_prob"][:16], s32["target_prob"], rtol=1e-4, atol=0)
     # no near-tie at all: nothing is refined, nothing changes
     eng0 = nib.PerturbationEngine(s["model"], s["x"], s["seg"], target=0, mode=nib.KEEP_MUL, precision="bf16", max_batch=64,
                                   S=50, refine_ties=1e-9, tie_capacity=16)

@@ -130,6 +130,88 @@ def test_conv_simt_vs_torch(nib, precision, case):
     assert err <= (1e-5 if precision == "fp32" else 1.2e-2) * scale
 
 
+def _one_split_conv(nib, Cin, Cout, k, stride, pad, H, relu, residual, N, seed):
+    """One conv on split-bf16 tensors (tcgen05 pair kernel, split mode) between two fp32 <-> split converts."""
+    from network_interpretation_imagenet_b200 import _lib
+    from network_interpretation_imagenet_b200.classifier import _Builder, Classifier, _out_hw
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    x = torch.randn(N, Cin, H, H, generator=g)
+    b = _Builder(_lib.PREC_SPLIT, N)
+    x_in = b.buffer(H, H, Cin, pooled=False, f32=True)
+    xs = b.buffer(H, H, Cin, pooled=False)
+    b.convert(x_in, xs)
+    Ho = _out_hw(H, k, stride, pad)
+    res_buf, wr = None, None
+    if residual:
+        res_buf = b.buffer(Ho, Ho, Cout, pooled=False)
+        wr = torch.randn(Cout, Cin, 1, 1, generator=g) / np.sqrt(Cin)
+        b.conv(xs, Cin, res_buf, Cout, wr, None, 1, stride, 0, relu=False)
+    out = b.buffer(Ho, Ho, Cout, pooled=False)
+    b.conv(xs, Cin, out, Cout, w, bias, k, stride, pad, relu=relu, res=res_buf, res_C=Cout if residual else 0)
+    of = b.buffer(Ho, Ho, Cout, pooled=False, f32=True)
+    b.convert(out, of)
+    feat = b.buffer(1, 1, Cout, f32=True)
+    b.pool(_lib.POOL_AVG, of, Cout, feat, Ho, Ho, 0)
+    b.fc(feat, Cout, 4, torch.zeros(4, Cout), None)
+    net = Classifier(b, x_in, (Cin, H, H), 4, "split", N, taps={"out": of})
+    net.forward(x.cuda())
+    got = net.read_tap("out", N).cpu().double()
+    ref = F.conv2d(x.double(), w.double(), bias.double(), stride=stride, padding=pad)
+    if residual:
+        ref = ref + F.conv2d(x.double(), wr.double(), None, stride=stride)
+    if relu:
+        ref = ref.clamp_min(0)
+    return got, ref, net
+
+
+SPLIT_CASES = [
+    # Cin, Cout, k, stride, pad, H, relu, residual
+    (64, 64, 1, 1, 0, 16, True, False),
+    (64, 64, 3, 1, 1, 16, True, False),
+    (64, 256, 1, 1, 0, 14, True, True),
+    (256, 64, 1, 1, 0, 14, True, False),
+    (128, 128, 3, 2, 1, 28, True, False),
+    (256, 256, 3, 1, 1, 14, True, False),
+    (256, 512, 1, 2, 0, 28, False, False),
+    (128, 512, 1, 1, 0, 9, True, True),
+    (512, 512, 3, 1, 1, 7, True, True),
+    (64, 128, 3, 1, 1, 33, True, True),          # ragged M (5 x 33 x 33 rows), BLOCK_N = 128 with residual
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=lambda c: "cin%d_cout%d_k%d_s%d_h%d_res%d" % (c[0], c[1], c[2], c[3], c[5], c[7]))
+def test_conv_split_tcgen05_vs_torch(nib, case):
+    """conv_tc3_kernel in split mode: activations [hi | lo], weights [Wh | Wh | Wl], both halves of the fp32 result stored
+    (and both halves of the residual added): fp32-grade against torch fp64."""
+    Cin, Cout, k, stride, pad, H, relu, residual = case
+    got, ref, net = _one_split_conv(nib, Cin, Cout, k, stride, pad, H, relu, residual, N=5, seed=sum(case[:6]))
+    total, tc = net.launch_counts()
+    assert tc == (2 if residual else 1), "the split convs did not take the tcgen05 path"
+    err = (got - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    assert err <= 3e-5 * scale, f"max abs err {err} (scale {scale})"
+
+
+def test_split_mode_resnets(nib):
+    """The tie policy's re-score lowering for torchvision ResNets: within the fp32 tolerance (1e-4) of the torch fp32 forward
+    and 5e-5 of the CUDA-core fp32 lowering, bottleneck (ResNet-101) and basic-block (ResNet-18) bodies."""
+    for arch, n in (("resnet101", 3), ("resnet18", 5)):
+        m = ocls.build_imagenet_model(arch)
+        x = torch.from_numpy(synthetic.synthetic_image("imagenet"))[None].repeat(n, 1, 1, 1)
+        x[1] = x[1].flip(2) * 0.5
+        x[2] = x[2] * (torch.rand(1, 224, 224, generator=torch.Generator().manual_seed(3)) > 0.5).float()
+        net, got, want = _check_net(nib, m, x, "split", TOL_FP32)
+        total, tc = net.launch_counts()
+        assert tc >= (100 if arch == "resnet101" else 19), (arch, tc)
+        ref32 = nib.Classifier.from_torch(m, (224, 224), precision="fp32", max_batch=n).forward(x.cuda()).cpu().numpy()
+        assert rel_err(got, ref32) <= 5e-5, arch
+        assert np.array_equal(got.argmax(1), ref32.argmax(1))
+    with pytest.raises(TypeError):
+        nib.Classifier.from_torch(ocls.load_resnet56(), (32, 32), precision="split", max_batch=4)
+
+
 X3_CASES = [
     # Cin, Cout, k, stride, pad, H,  W,  relu, residual
     (16, 16, 3, 1, 1, 32, 32, True, True),       # ResNet-56 stage 1 (K = 144: half a slab of tail)
