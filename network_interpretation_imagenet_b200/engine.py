@@ -150,39 +150,42 @@ class PerturbationEngine:
         self._bufs: dict = {}
 
     # -- tie policy ------------------------------------------------------------------------------------
-    def _fp32_classifier(self) -> Classifier:
-        if self._fp32 is None:
-            self._fp32 = Classifier.from_torch(self._model_src, (self.synth.H, self.synth.W), precision=self.tie_precision,
-                                               max_batch=self.tie_capacity)
-        return self._fp32
-
-    def _tie_state(self):
-        if self._tie is None:
-            dev, cap = self.device, self.tie_capacity
-            f32 = self._fp32_classifier()
-            t = {"idx": torch.full((cap,), -1, dtype=torch.int32, device=dev),
-                 "sel": torch.zeros(cap, self.synth.words, dtype=torch.int64, device=dev),
-                 "count": torch.zeros(1, dtype=torch.int32, device=dev),
-                 "logits": torch.zeros(cap, f32.num_classes, dtype=torch.float32, device=dev),
-                 "totals": torch.zeros(2, dtype=torch.int64, device=dev)}   # (near-ties, did not fit), read by tie_stats()
-            t["score"] = {"top1": torch.empty(cap, dtype=torch.int32, device=dev),
-                          "target_prob": torch.empty(cap, dtype=torch.float32, device=dev),
-                          "max_prob": torch.empty(cap, dtype=torch.float32, device=dev),
-                          "correct": torch.empty(cap, dtype=torch.uint8, device=dev),
-                          "margin": torch.empty(cap, dtype=torch.float32, device=dev)}
-            _lib.check(self.lib.nib_net_set_dynamic_batch(f32.h, t["count"].data_ptr()), "nib_net_set_dynamic_batch")
-            self._tie = t
-        return self._tie
+    def _tie_state(self, n: int):
+        """Buffers and the re-score lowering for a window of `n` masks: at most `tie_capacity` rows, but no larger than the
+        window itself (a 16-mask call does not need a 640-image network); grown, never shrunk."""
+        cap = min(self.tie_capacity, max(8, int(n)))
+        if self._tie is not None and self._tie["cap"] >= cap:
+            return self._tie
+        totals = self._tie["totals"] if self._tie is not None else torch.zeros(2, dtype=torch.int64, device=self.device)
+        if self._tie is not None:
+            torch.cuda.current_stream().synchronize()       # the smaller lowering may still be running
+        self._tie = self._fp32 = None
+        dev = self.device
+        f32 = Classifier.from_torch(self._model_src, (self.synth.H, self.synth.W), precision=self.tie_precision, max_batch=cap)
+        t = {"cap": cap, "net": f32,
+             "idx": torch.full((cap,), -1, dtype=torch.int32, device=dev),
+             "sel": torch.zeros(cap, self.synth.words, dtype=torch.int64, device=dev),
+             "count": torch.zeros(1, dtype=torch.int32, device=dev),
+             "logits": torch.zeros(cap, f32.num_classes, dtype=torch.float32, device=dev),
+             "totals": totals}   # (near-ties, did not fit), read by tie_stats()
+        t["score"] = {"top1": torch.empty(cap, dtype=torch.int32, device=dev),
+                      "target_prob": torch.empty(cap, dtype=torch.float32, device=dev),
+                      "max_prob": torch.empty(cap, dtype=torch.float32, device=dev),
+                      "correct": torch.empty(cap, dtype=torch.uint8, device=dev),
+                      "margin": torch.empty(cap, dtype=torch.float32, device=dev)}
+        _lib.check(self.lib.nib_net_set_dynamic_batch(f32.h, t["count"].data_ptr()), "nib_net_set_dynamic_batch")
+        self._tie, self._fp32 = t, f32
+        return t
 
     def _refine(self, d_sel: torch.Tensor, s: dict, table: torch.Tensor | None, synth: MaskSynth):
         """Device-side tie policy on the scores `s` of the rows `d_sel` (no host sync)."""
-        t = self._tie_state()
-        n, cap = int(d_sel.shape[0]), self.tie_capacity
+        n = int(d_sel.shape[0])
+        t = self._tie_state(n)
+        cap, f32 = t["cap"], t["net"]
         st = _lib.stream_handle()
         _lib.check(self.lib.nib_tie_compact(s["margin"].data_ptr(), n, self.refine_ties, d_sel.data_ptr(), self.synth.words,
                                             cap, t["idx"].data_ptr(), t["sel"].data_ptr(), t["count"].data_ptr(),
                                             t["totals"].data_ptr(), st), "nib_tie_compact")
-        f32 = self._fp32_classifier()
         f32.forward_masked(synth, t["sel"], self.mode, out=t["logits"])
         score(t["logits"], self.target, out=t["score"])
         r = t["score"]
