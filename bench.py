@@ -379,8 +379,9 @@ def run_ours(args):
 
     def all_launches():
         a, b = clf.launch_counts()
-        if eng._fp32 is not None:
-            a += eng._fp32.launch_counts()[0]
+        if eng._fp32 is not None:           # the tie policy's re-score lowering
+            a2, b2 = eng._fp32.launch_counts()
+            a, b = a + a2, b + b2
         return a, b
 
     for _ in range(args.warmup):

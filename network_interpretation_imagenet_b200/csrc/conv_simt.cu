@@ -252,6 +252,45 @@ __global__ void pool_kernel(PoolParams p) {
   Elem<T>::st(out + (((size_t)n * p.P + pp) * p.Q + q) * p.out_cstride + p.out_coff + c, acc);
 }
 
+// 4 fp32 channels (one 128-bit load/store) per thread; no pre-activation.  The fp32 / split networks' max-pool and global
+// average pool (the scalar kernel above spent 260 us on the 80-image re-score batch of the tie policy).
+__global__ void __launch_bounds__(256)
+pool_f32x4_kernel(PoolParams p) {
+  const float* __restrict__ in = reinterpret_cast<const float*>(p.in);
+  float* __restrict__ out = reinterpret_cast<float*>(p.out);
+  const int C4 = p.C >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Nl = p.dyn_n ? min(max(*p.dyn_n, 0), p.N) : p.N;
+  long long total = (long long)Nl * p.P * p.Q * C4;
+  if (idx >= total) return;
+  const int c = (int)(idx % C4) * 4;
+  long long t = idx / C4;
+  const int q = (int)(t % p.Q); t /= p.Q;
+  const int pp = (int)(t % p.P);
+  const int n = (int)(t / p.P);
+  const float init = p.kind == NIB_POOL_MAX ? -INFINITY : 0.f;
+  float4 acc = make_float4(init, init, init, init);
+  for (int r = 0; r < p.k; ++r) {
+    const int ih = pp * p.stride - p.pad + r;
+    if (ih < 0 || ih >= p.Hin) continue;
+    for (int s = 0; s < p.k; ++s) {
+      const int iw = q * p.stride - p.pad + s;
+      if (iw < 0 || iw >= p.Win) continue;
+      const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)n * p.Hin + ih) * p.Win + iw) * p.in_cstride + p.in_coff + c);
+      if (p.kind == NIB_POOL_MAX) {
+        acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+      } else {
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+  }
+  if (p.kind == NIB_POOL_AVG) {
+    const float d = (float)(p.k * p.k);
+    acc.x = acc.x / d; acc.y = acc.y / d; acc.z = acc.z / d; acc.w = acc.w / d;
+  }
+  *reinterpret_cast<float4*>(out + (((size_t)n * p.P + pp) * p.Q + q) * p.out_cstride + p.out_coff + c) = acc;
+}
+
 // 8 bf16 channels (one 128-bit load/store) per thread; no pre-activation.
 __global__ void __launch_bounds__(256)
 pool_bf16x8_kernel(PoolParams p) {
@@ -308,6 +347,13 @@ int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st) {
       p.out_cstride % 8 == 0 && p.out_coff % 8 == 0) {
     long long total8 = (long long)p.N * p.P * p.Q * (p.C / 8);
     pool_bf16x8_kernel<<<(unsigned)ceil_div_ll(total8, 256), 256, 0, st>>>(p);
+    NIB_LAUNCH_CHECK();
+    return NIB_OK;
+  }
+  if (!bf16 && p.pre_scale == nullptr && p.C % 4 == 0 && p.in_cstride % 4 == 0 && p.in_coff % 4 == 0 &&
+      p.out_cstride % 4 == 0 && p.out_coff % 4 == 0) {
+    long long total4 = (long long)p.N * p.P * p.Q * (p.C / 4);
+    pool_f32x4_kernel<<<(unsigned)ceil_div_ll(total4, 256), 256, 0, st>>>(p);
     NIB_LAUNCH_CHECK();
     return NIB_OK;
   }
@@ -492,9 +538,11 @@ int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int 
 // Boundaries of a NIB_PREC_SPLIT network (conv_tc.cu split mode): the stem and the pooled features are fp32, the body's
 // tensors carry each value as two bf16 halves in the channel dimension.  4 channels per thread.
 __global__ void __launch_bounds__(256)
-split_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long M, int C) {
+split_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long M, int C, const int* __restrict__ dyn_n,
+                  int rows_per_image) {
   const int g = C >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dyn_n != nullptr) M = min(M, (long long)max(*dyn_n, 0) * rows_per_image);
   if (idx >= M * g) return;
   const long long m = idx / g;
   const int c = (int)(idx - m * g) << 2;
@@ -510,9 +558,11 @@ split_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, lo
   *reinterpret_cast<uint2*>(y + m * 2 * C + C + c) = *reinterpret_cast<const uint2*>(lo);
 }
 __global__ void __launch_bounds__(256)
-split_merge_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long M, int C) {
+split_merge_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long M, int C, const int* __restrict__ dyn_n,
+                   int rows_per_image) {
   const int g = C >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dyn_n != nullptr) M = min(M, (long long)max(*dyn_n, 0) * rows_per_image);
   if (idx >= M * g) return;
   const long long m = idx / g;
   const int c = (int)(idx - m * g) << 2;
@@ -524,15 +574,15 @@ split_merge_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, l
   o.z = __bfloat162float(hb[2]) + __bfloat162float(lb[2]); o.w = __bfloat162float(hb[3]) + __bfloat162float(lb[3]);
   *reinterpret_cast<float4*>(y + m * C + c) = o;
 }
-int launch_split_convert(const void* in, void* out, long long M, int C, bool to_split, const int* dyn_n, cudaStream_t st) {
-  (void)dyn_n;   // a handful of extra rows cost less than reading the count
+int launch_split_convert(const void* in, void* out, long long M, int C, bool to_split, const int* dyn_n, int rows_per_image,
+                         cudaStream_t st) {
   NIB_REQUIRE(C % 4 == 0, "split convert: C = %d is not a multiple of 4", C);
   const long long total = M * (C >> 2);
   const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
   if (to_split)
-    split_pack_kernel<<<blocks, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, M, C);
+    split_pack_kernel<<<blocks, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, M, C, dyn_n, rows_per_image);
   else
-    split_merge_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, M, C);
+    split_merge_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, M, C, dyn_n, rows_per_image);
   NIB_LAUNCH_CHECK();
   return NIB_OK;
 }

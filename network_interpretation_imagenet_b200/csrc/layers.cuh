@@ -53,8 +53,10 @@ int launch_nchw_to_nhwc(const float* x, int N, int C, int H, int W, void* out, i
 int launch_nhwc_to_nchw(const void* in, int N, int C, int H, int W, int cs, int halo, bool bf16, float* out,
                         cudaStream_t st);
 // fp32 [M][C] <-> split bf16 [M][hi(C) | lo(C)], x = hi + lo with hi = bf16(x), lo = bf16(x - hi)   (NIB_PREC_SPLIT)
-int launch_split_convert(const void* in, void* out, long long M, int C, bool to_split, const int* dyn_n, cudaStream_t st);
-int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo);
+int launch_split_convert(const void* in, void* out, long long M, int C, bool to_split, const int* dyn_n, int rows_per_image,
+                         cudaStream_t st);
+// dyn_n: optional device-side live mask count (<= a->N); masks beyond it are not synthesised
+int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo, const int* dyn_n = nullptr);
 
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ---------------------------------------------
 struct TcConvPlan;  // opaque: tensor maps + tile configuration for one conv layer

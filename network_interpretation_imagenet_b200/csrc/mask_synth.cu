@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256)
 mask_synth_kernel(const float* __restrict__ img, const LabT* __restrict__ labels,
                   const uint64_t* __restrict__ sel, int words, int N, int C, int H, int W,
                   const float* __restrict__ seg_minmax, int S, OutT* __restrict__ out, int c_stride, int pad_h,
-                  int pad_w, uint8_t* __restrict__ pixel_mask, int masks_per_cta) {
+                  int pad_w, uint8_t* __restrict__ pixel_mask, int masks_per_cta, const int* __restrict__ dyn_n) {
+  if (dyn_n != nullptr) N = min(N, max(*dyn_n, 0));   // device-side live mask count (tie policy re-score batch)
   constexpr int kStatChunk = 256;   // == blockDim.x: one thread computes the (min, max - min) of one mask of the chunk
   __shared__ float2 s_stats[MODE == NIB_MASK_REMOVE_MINMAX ? kStatChunk : 1];
   const int HW = H * W;
@@ -211,7 +212,9 @@ template <int MODE, typename LabT>
 __global__ void __launch_bounds__(256)
 mask_synth_nhwc4_kernel(const float* __restrict__ img, const LabT* __restrict__ labels, const uint64_t* __restrict__ sel,
                         int words, int N, int C, int H, int W, const float* __restrict__ seg_minmax, int S,
-                        __nv_bfloat16* __restrict__ out, int pad, uint8_t* __restrict__ pixel_mask, int masks_per_cta) {
+                        __nv_bfloat16* __restrict__ out, int pad, uint8_t* __restrict__ pixel_mask, int masks_per_cta,
+                        const int* __restrict__ dyn_n) {
+  if (dyn_n != nullptr) N = min(N, max(*dyn_n, 0));
   constexpr int kStatChunk = 256;
   __shared__ float2 s_stats[MODE == NIB_MASK_REMOVE_MINMAX ? kStatChunk : 1];
   const int Wp = W + 2 * pad, Hp = H + 2 * pad;
@@ -484,7 +487,7 @@ __global__ void heat_scatter_kernel(const LabT* __restrict__ labels, int HW, int
 }
 
 template <typename OutT, int LAYOUT, int MODE, typename LabT>
-static int launch_mask(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
+static int launch_mask(const nib_mask_args* a, bool skip_halo, const int* dyn_n, cudaStream_t st) {
   const int HW = a->H * a->W;
   if (LAYOUT == NIB_NHWC && sizeof(OutT) == 2 && a->c_stride == 4 && a->pad_h == a->pad_w && a->pad_w > 0 &&
       ((a->W + 2 * a->pad_w) % 2) == 0) {
@@ -496,7 +499,7 @@ static int launch_mask(const nib_mask_args* a, bool skip_halo, cudaStream_t st) 
     gy = ceil_div(a->N, mpc);
     mask_synth_nhwc4_kernel<MODE, LabT><<<dim3(gx, gy), 256, 0, st>>>(
         a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, a->d_seg_minmax, a->S,
-        (__nv_bfloat16*)a->d_out, a->pad_w, a->d_pixel_mask, mpc);
+        (__nv_bfloat16*)a->d_out, a->pad_w, a->d_pixel_mask, mpc, dyn_n);
     NIB_LAUNCH_CHECK();
     if (!skip_halo) {   // only the top / bottom halo rows remain (the side columns were written above); the generic
                         // kernel covers them, re-zeroing the sides as well
@@ -521,11 +524,11 @@ static int launch_mask(const nib_mask_args* a, bool skip_halo, cudaStream_t st) 
   if (vec4)
     mask_synth_kernel<OutT, LAYOUT, MODE, 4, LabT><<<grid, threads, 0, st>>>(
         a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, a->d_seg_minmax, a->S,
-        (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc);
+        (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc, dyn_n);
   else
     mask_synth_kernel<OutT, LAYOUT, MODE, 1, LabT><<<grid, threads, 0, st>>>(
         a->d_img, (const LabT*)a->d_labels, a->d_sel, a->sel_words, a->N, a->C, a->H, a->W, a->d_seg_minmax, a->S,
-        (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc);
+        (OutT*)a->d_out, a->c_stride, a->pad_h, a->pad_w, a->d_pixel_mask, mpc, dyn_n);
   NIB_LAUNCH_CHECK();
   if (LAYOUT == NIB_NHWC && (a->pad_h > 0 || a->pad_w > 0) && !skip_halo) {
     const int Hp = a->H + 2 * a->pad_h, Wp = a->W + 2 * a->pad_w;
@@ -538,19 +541,19 @@ static int launch_mask(const nib_mask_args* a, bool skip_halo, cudaStream_t st) 
 }
 
 template <typename OutT, int LAYOUT, typename LabT>
-static int dispatch_mode(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
-  if (a->mode == NIB_MASK_KEEP_MUL) return launch_mask<OutT, LAYOUT, NIB_MASK_KEEP_MUL, LabT>(a, skip_halo, st);
-  return launch_mask<OutT, LAYOUT, NIB_MASK_REMOVE_MINMAX, LabT>(a, skip_halo, st);
+static int dispatch_mode(const nib_mask_args* a, bool skip_halo, const int* dyn_n, cudaStream_t st) {
+  if (a->mode == NIB_MASK_KEEP_MUL) return launch_mask<OutT, LAYOUT, NIB_MASK_KEEP_MUL, LabT>(a, skip_halo, dyn_n, st);
+  return launch_mask<OutT, LAYOUT, NIB_MASK_REMOVE_MINMAX, LabT>(a, skip_halo, dyn_n, st);
 }
 template <typename OutT, typename LabT>
-static int dispatch_layout(const nib_mask_args* a, bool skip_halo, cudaStream_t st) {
-  if (a->layout == NIB_NCHW) return dispatch_mode<OutT, NIB_NCHW, LabT>(a, skip_halo, st);
-  return dispatch_mode<OutT, NIB_NHWC, LabT>(a, skip_halo, st);
+static int dispatch_layout(const nib_mask_args* a, bool skip_halo, const int* dyn_n, cudaStream_t st) {
+  if (a->layout == NIB_NCHW) return dispatch_mode<OutT, NIB_NCHW, LabT>(a, skip_halo, dyn_n, st);
+  return dispatch_mode<OutT, NIB_NHWC, LabT>(a, skip_halo, dyn_n, st);
 }
 
 // skip_halo: the caller guarantees the halo ring of d_out already holds +0 (the network's own input buffer is zeroed
 // when it is allocated and nothing else ever writes its halo), so it is not re-written on every forward.
-int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo) {
+int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo, const int* dyn_n) {
   NIB_REQUIRE(a != nullptr, "nib_mask_synth: null args");
   if (a->N == 0) return NIB_OK;  // an empty batch is legal (and its tensors have null data pointers)
   NIB_REQUIRE(a->d_img && a->d_labels && a->d_sel && a->d_out, "nib_mask_synth: null device pointer");
@@ -568,11 +571,11 @@ int mask_synth_impl(const nib_mask_args* a, cudaStream_t st, bool skip_halo) {
   if (a->mode == NIB_MASK_REMOVE_MINMAX)
     NIB_REQUIRE(a->d_seg_minmax != nullptr, "nib_mask_synth: REMOVE_MINMAX needs d_seg_minmax (nib_segment_minmax)");
   if (a->out_dtype == NIB_F32) {
-    if (a->label_bytes == 1) return dispatch_layout<float, uint8_t>(a, skip_halo, st);
-    return dispatch_layout<float, uint16_t>(a, skip_halo, st);
+    if (a->label_bytes == 1) return dispatch_layout<float, uint8_t>(a, skip_halo, dyn_n, st);
+    return dispatch_layout<float, uint16_t>(a, skip_halo, dyn_n, st);
   } else {
-    if (a->label_bytes == 1) return dispatch_layout<__nv_bfloat16, uint8_t>(a, skip_halo, st);
-    return dispatch_layout<__nv_bfloat16, uint16_t>(a, skip_halo, st);
+    if (a->label_bytes == 1) return dispatch_layout<__nv_bfloat16, uint8_t>(a, skip_halo, dyn_n, st);
+    return dispatch_layout<__nv_bfloat16, uint16_t>(a, skip_halo, dyn_n, st);
   }
 }
 
@@ -582,7 +585,7 @@ extern "C" {
 
 int nib_mask_synth(const nib_mask_args* args, void* stream) {
   NIB_DEVICE_OR_FAIL();
-  return nib::mask_synth_impl(args, (cudaStream_t)stream, false);
+  return nib::mask_synth_impl(args, (cudaStream_t)stream, false, nullptr);
 }
 
 int nib_segment_minmax(const float* d_img, const void* d_labels, int label_bytes, int C, int H, int W,

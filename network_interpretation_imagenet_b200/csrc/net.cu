@@ -522,7 +522,7 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
     } else if (op.kind == 3) {
       const NetBuffer& bi = net->bufs[op.in_buf];
       const NetBuffer& bo = net->bufs[op.out_buf];
-      int rc = launch_split_convert(bi.ptr, bo.ptr, (long long)N * bi.H * bi.W, bi.C, bi.kind == BUF_F32, net->dyn_n, st);
+      int rc = launch_split_convert(bi.ptr, bo.ptr, (long long)N * bi.H * bi.W, bi.C, bi.kind == BUF_F32, net->dyn_n, bi.H * bi.W, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
     } else if (op.kind == 1) {
@@ -698,7 +698,7 @@ int nib_net_forward_masked(nib_net* net, const nib_mask_args* args, float* d_log
   a.c_stride = bi.C;
   a.pad_h = a.pad_w = bi.pad;
   // the input buffer's halo ring was zeroed by nib_net_add_buffer and no op writes it: skip the per-forward re-zeroing
-  int rc = mask_synth_impl(&a, (cudaStream_t)stream, true);
+  int rc = mask_synth_impl(&a, (cudaStream_t)stream, true, net->dyn_n);
   net->launches += 1;
   if (rc != NIB_OK) return rc;
   return nib_net_forward(net, bi.ptr, NIB_IN_NATIVE, args->N, d_logits, stream);
