@@ -466,7 +466,7 @@ static inline int split64(int w) { return ((w / 2 + NB - 1) / NB) * NB; }   // N
 // (right-looking, the update order of LAPACK dpotf2 that scipy.linalg.cholesky ends in, _gpr.py:352).
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restrict__ info, double* __restrict__ dinv) {
-  __shared__ double colbuf[2][NB];
+  __shared__ __align__(16) double colbuf[2][NB];
   __shared__ double rdiag[NB];
   extern __shared__ __align__(16) double pd_smem[];   // the factored block and its inverse (dinv != null), TRTRI_SMEM bytes
   double (*Lsh)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(pd_smem);
@@ -481,44 +481,53 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int nb, int* __restric
       const int i = 4 * br + a, j = 4 * bc + b;
       r[a][b] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : ((i == j) ? 1.0 : 0.0);   // identity padding
     }
-  for (int j = 0; j < NB; ++j) {
-    const int cb = j >> 2, cj = j & 3;
-    double* col = colbuf[j & 1];
-    if (bc == cb) {
+  // The pivot loop is bound by the number of instructions each warp issues per pivot (two warps per scheduler, every
+  // instruction waiting on the one before): with the update predicated per element it was ~240 instructions and 1400
+  // cycles per pivot.  Here the 16 FMAs are unconditional — the scaled column is zeroed for the columns that are
+  // already final, and the strictly upper part of the block carries values nothing reads — and the column index is a
+  // compile-time constant (j = 4 jb + cj, cj unrolled).
+  for (int jb = 0; jb < NB / 4; ++jb) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        double v = r[a][0];
-        if (cj == 1) v = r[a][1];
-        if (cj == 2) v = r[a][2];
-        if (cj == 3) v = r[a][3];
-        col[4 * br + a] = v;
+    for (int cj = 0; cj < 4; ++cj) {
+      const int j = 4 * jb + cj;
+      double* col = colbuf[cj & 1];
+      if (bc == jb) {
+        *reinterpret_cast<double2*>(col + 4 * br) = make_double2(r[0][cj], r[1][cj]);
+        *reinterpret_cast<double2*>(col + 4 * br + 2) = make_double2(r[2][cj], r[3][cj]);
+      }
+      __syncthreads();
+      const double d = col[j];
+      if (!(d > 0.0)) {  // also catches NaN; uniform across the block
+        if (tid == 0 && *info == 0) *info = k0 + j + 1;
+        return;
+      }
+      // one reciprocal square root instead of a square root followed by a division (CUDA's double rsqrt: 1 ulp)
+      const double inv = rsqrt(d);
+      if (tid == 0) rdiag[j] = inv;     // = 1 / L[j][j], reused by the inverse
+      const double2 c01 = *reinterpret_cast<const double2*>(col + 4 * br);
+      const double2 c23 = *reinterpret_cast<const double2*>(col + 4 * br + 2);
+      const double2 k01 = *reinterpret_cast<const double2*>(col + 4 * bc);
+      const double2 k23 = *reinterpret_cast<const double2*>(col + 4 * bc + 2);
+      const double lr[4] = {c01.x * inv, c01.y * inv, c23.x * inv, c23.y * inv};
+      double lc[4] = {k01.x * inv, k01.y * inv, k23.x * inv, k23.y * inv};
+      if (bc < jb) { lc[0] = 0.0; lc[1] = 0.0; lc[2] = 0.0; lc[3] = 0.0; }
+      if (bc == jb) {
+#pragma unroll
+        for (int b = 0; b <= cj; ++b) lc[b] = 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r[a][b] = fma(-lr[a], lc[b], r[a][b]);
+      if (bc == jb) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int i = 4 * br + a;
+          if (i > j) r[a][cj] = lr[a];
+          if (i == j) r[a][cj] = d * inv;
+        }
       }
     }
-    __syncthreads();
-    const double d = col[j];
-    if (!(d > 0.0)) {  // also catches NaN; uniform across the block
-      if (tid == 0 && *info == 0) *info = k0 + j + 1;
-      return;
-    }
-    // one reciprocal square root instead of a square root followed by a division: the pivot chain is
-    // 64 steps long and every dependent fp64 operation on it costs ~48 cycles
-    const double inv = rsqrt(d);      // CUDA's double rsqrt is accurate to 1 ulp
-    const double rs = d * inv;
-    if (tid == 0) rdiag[j] = inv;     // = 1 / L[j][j], reused by the inverse
-    double lr[4], lc[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      lr[a] = col[4 * br + a] * inv;
-      lc[a] = col[4 * bc + a] * inv;
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int i = 4 * br + a, k = 4 * bc + b;
-        if (k > j && i >= k) r[a][b] = fma(-lr[a], lc[b], r[a][b]);
-        if (k == j) r[a][b] = (i > j) ? lr[a] : ((i == j) ? rs : r[a][b]);
-      }
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -717,11 +726,162 @@ trsv_step_kernel(const double* __restrict__ Lm, int ldl, double* __restrict__ b,
   }
 }
 
+// Wavefront form of the same solve: ONE launch, one thread block per 64-row block of L.  Block i accumulates
+// L[i][k] x_k (L^T: L[k][i]^T x_k) for its dependencies k in the order they finish, then multiplies by the inverse
+// diagonal block and publishes x_i.  There is no flag: the solved vector goes to a scratch copy that starts out as a
+// sentinel bit pattern (all ones, a NaN no computation produces: NaN results are canonicalised before the store), and
+// warp 0 of every waiting block polls the 64 values it needs until none is the sentinel — data and "ready" arrive in the
+// same L2 round trip.  The L tile of the next dependency is already in registers when x_k arrives, so a chain step is
+// one L2 round trip, two 4-deep FMA chains and two block barriers instead of a kernel launch (128 launches of ~10 us
+// at n = 8192 before; 0.77 / 0.49 ms per solve with an acquire flag + fence per step).
+// Forward progress: block i only waits on blocks the hardware dispatched before it (blockIdx order follows the dependency
+// order in both directions), so the lowest unfinished block is always resident; the spin is bounded and traps.
+static constexpr unsigned long long TRSV_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ void wave_fetch(const double* xw, int k, int n, double* dst) {
+  // warp 0: lane owns entries lane and lane + 32 of block k
+  const int lane = threadIdx.x;
+  const int r0 = k * NB + lane, r1 = r0 + 32;
+  const volatile unsigned long long* p = reinterpret_cast<const volatile unsigned long long*>(xw);
+  unsigned long long v0 = 0ull, v1 = 0ull;
+  unsigned spins = 0;
+  for (;;) {
+    v0 = r0 < n ? p[r0] : 0ull;
+    v1 = r1 < n ? p[r1] : 0ull;
+    if (__all_sync(0xffffffffu, v0 != TRSV_SENTINEL && v1 != TRSV_SENTINEL)) break;
+    if (++spins > 256u) __nanosleep(20);
+    if (spins > (1u << 26)) __trap();
+  }
+  dst[lane] = __longlong_as_double((long long)v0);
+  dst[lane + 32] = __longlong_as_double((long long)v1);
+}
+
+__global__ void __launch_bounds__(256)
+trsv_wave_kernel(const double* __restrict__ Lm, int ldl, double* __restrict__ b, int n, int trans,
+                 const double* __restrict__ dinv, double* xw) {
+  __shared__ double Ds[NB][NB + 1];
+  __shared__ double part[4][NB];
+  __shared__ double bs[NB];
+  __shared__ double xs[2][NB];
+  const int tid = threadIdx.x;
+  const int nblk = (n + NB - 1) / NB;
+  const int blk = trans ? nblk - 1 - (int)blockIdx.x : (int)blockIdx.x;
+  const int k0 = blk * NB;
+  const int nb = min(NB, n - k0);
+  {
+    const double* D = dinv + (size_t)blk * NB * NB;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int idx = tid + e * 256, a = idx >> 6, c = idx & 63;
+      const double v = D[idx];
+      if (trans) Ds[c][a] = v; else Ds[a][c] = v;              // Ds = inv(Lkk) or its transpose
+    }
+  }
+  const int ndeps = (int)blockIdx.x;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  double l[16];
+  if (!trans) {
+    // thread (row, q): 16 consecutive columns of row k0+row in block column k
+    const int row = tid >> 2, q = tid & 3;
+    const bool live = row < nb;
+    const double* base = Lm + (size_t)(k0 + (live ? row : 0)) * ldl + q * 16;
+    if (ndeps > 0) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) l[t] = live ? __ldg(base + t) : 0.0;
+    }
+    for (int k = 0; k < ndeps; ++k) {
+      if (tid < 32) wave_fetch(xw, k, n, xs[k & 1]);
+      __syncthreads();
+      const double* xv = xs[k & 1] + q * 16;
+#pragma unroll
+      for (int t = 0; t < 16; t += 4) {
+        acc0 = fma(l[t], xv[t], acc0);
+        acc1 = fma(l[t + 1], xv[t + 1], acc1);
+        acc2 = fma(l[t + 2], xv[t + 2], acc2);
+        acc3 = fma(l[t + 3], xv[t + 3], acc3);
+      }
+      if (k + 1 < ndeps) {
+        const double* nx = base + (size_t)(k + 1) * NB;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) l[t] = live ? __ldg(nx + t) : 0.0;
+      }
+    }
+    double acc = (acc0 + acc1) + (acc2 + acc3);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) bs[row] = live ? b[k0 + row] - acc : 0.0;
+  } else {
+    // thread (c, tq): column k0+c of rows k*NB + tq*16 .. +16 (coalesced along c)
+    const int c = tid & 63, tq = tid >> 6;
+    const bool live = c < nb;
+    const double* base = Lm + k0 + (live ? c : 0);
+    auto load_tile = [&](int k) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int r = k * NB + tq * 16 + t;
+        l[t] = (live && r < n) ? __ldg(base + (size_t)r * ldl) : 0.0;
+      }
+    };
+    if (ndeps > 0) load_tile(nblk - 1);
+    for (int s = 0; s < ndeps; ++s) {
+      const int k = nblk - 1 - s;
+      if (tid < 32) wave_fetch(xw, k, n, xs[s & 1]);
+      __syncthreads();
+      const double* xv = xs[s & 1] + tq * 16;
+#pragma unroll
+      for (int t = 0; t < 16; t += 4) {
+        acc0 = fma(l[t], xv[t], acc0);
+        acc1 = fma(l[t + 1], xv[t + 1], acc1);
+        acc2 = fma(l[t + 2], xv[t + 2], acc2);
+        acc3 = fma(l[t + 3], xv[t + 3], acc3);
+      }
+      if (s + 1 < ndeps) load_tile(k - 1);
+    }
+    part[tq][c] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (tid < NB) bs[tid] = tid < nb ? b[k0 + tid] - ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid])) : 0.0;
+  }
+  __syncthreads();
+  {
+    const int row = tid >> 2, q = tid & 3;
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 16; t += 4) {
+      x0 = fma(Ds[row][q * 16 + t], bs[q * 16 + t], x0);
+      x1 = fma(Ds[row][q * 16 + t + 1], bs[q * 16 + t + 1], x1);
+      x2 = fma(Ds[row][q * 16 + t + 2], bs[q * 16 + t + 2], x2);
+      x3 = fma(Ds[row][q * 16 + t + 3], bs[q * 16 + t + 3], x3);
+    }
+    double x = (x0 + x1) + (x2 + x3);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    if (q == 0 && row < nb) {
+      if (x != x) x = __longlong_as_double(0x7ff8000000000000ll);   // never the sentinel
+      __stcg(xw + k0 + row, x);
+      b[k0 + row] = x;
+    }
+  }
+}
+
+static bool trsv_wave_on() {
+  static const bool v = getenv("NIB_GP_TRSV_STEPS") == nullptr;   // A/B switch: the one-launch-per-block form
+  return v;
+}
+
 static int trsv_impl(const double* L, int n, int ldl, double* b, int trans, const double* dinv, cudaStream_t st) {
+  const int nblk = ceil_div(n, NB);
+  if (dinv != nullptr && trsv_wave_on()) {
+    double* xw = nullptr;
+    int rcf = stream_scratch(SCRATCH_GP_TRSV, st, (size_t)n * sizeof(double), 16384 * sizeof(double), reinterpret_cast<void**>(&xw));
+    if (rcf != NIB_OK) return rcf;
+    NIB_CUDA(cudaMemsetAsync(xw, 0xFF, (size_t)n * sizeof(double), st));
+    trsv_wave_kernel<<<nblk, 256, 0, st>>>(L, ldl, b, n, trans, dinv, xw);
+    NIB_LAUNCH_CHECK();
+    return NIB_OK;
+  }
   double* g_trsv_x = nullptr;
   int rcs = stream_scratch(SCRATCH_GP_TRSV, st, (size_t)n * sizeof(double), 16384 * sizeof(double), reinterpret_cast<void**>(&g_trsv_x));
   if (rcs != NIB_OK) return rcs;
-  const int nblk = ceil_div(n, NB);
   for (int s = 0; s < nblk; ++s) {
     const int blk = trans ? nblk - 1 - s : s;
     const int k0 = blk * NB;
