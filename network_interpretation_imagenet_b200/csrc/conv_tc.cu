@@ -67,6 +67,11 @@ struct TcKernelParams {
   int lo_off_res;            // ... and in the residual tensor
   const int* dyn_n;          // split mode: optional device-side live image count (the tie policy's re-score batch); tiles
                              // beyond live * P * Q rows are not computed
+  // im2col == 4 (3x3 stride-1 pad-1, 64 -> 64 channels): an M tile is halo_r whole image rows in the raster of the PADDED
+  // width halo_wp = Q + 2; the (halo_r + 2) x halo_wp input patch is loaded once and all nine taps read it at shifted
+  // start addresses
+  int halo_wp, halo_r, halo_tpi;   // padded width, image rows per tile, tiles per image
+  int halo_swap;                   // im2col == 5 diagnostics: swap the LBO / SBO roles of the unswizzled descriptor
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -169,6 +174,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;  // SBO
   d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+// K-major, unswizzled: core matrices of 8 rows x 16 B (128 contiguous bytes); lbo = distance between core matrices along K,
+// sbo = between 8-row groups.  With lbo = 16 and sbo = 128 row r starts 16 r bytes into the buffer and its K run simply
+// continues: overlapping rows, which is exactly a stride-2 window over 8-byte pixels (the stem, im2col mode 5).
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 
@@ -698,7 +715,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0) mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(2 * p.num_k_blocks * SM::BH_BYTES));
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const uint32_t dst = smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES;
-          if (p.im2col == 3) {   // 64B-swizzled: the K block is two 32-element atoms
+          if (p.im2col == 3 || p.im2col == 5) {   // 64B-swizzled: the K block is two 32-element atoms
             tma2_load_2d(dst, &tmB, lb, kb * TC_BLOCK_K, b_row0);
             tma2_load_2d(dst + SM::BH_BYTES / 2, &tmB, lb, kb * TC_BLOCK_K + 32, b_row0);
           } else {
@@ -725,6 +742,31 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else if (p.im2col >= 2) {
         img = m_tile / p.P;
         h0 = (m_tile - img * p.P) * p.stride;
+      }
+      if (BRES && !HAS_RES && p.im2col == 4) {
+        // halo patch: ONE 4D tiled load per tile (rows y0-1 .. y0+halo_r, columns -1 .. Q; out-of-range coordinates are
+        // zero-filled = the convolution's padding) into one of four 32 KB buffers (ring stages 0, 2, 4, 6)
+        const int st4 = 2 * (it & 3);
+        TC3_TIMED(0, mbar_wait(empty_bar(st4), (uint32_t)(((it >> 2) & 1) ^ 1), p.err_flag, 1));
+        if (elect_one()) {
+          const int im = m_tile / p.halo_tpi;
+          const int y0 = (m_tile - im * p.halo_tpi) * p.halo_r;
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(st4), (uint32_t)(2 * p.a_bytes));
+          tma2_load_4d(smem_base + st4 * SM::STAGE_BYTES, &tmA, lbar0 + 8u * st4, p.in_coff, -1, y0 - 1, im);
+        }
+        __syncwarp();
+        continue;
+      }
+      if (BRES && !HAS_RES && p.im2col == 5) {
+        // stem: the seven padded input rows under one output row, raw (7 x row bytes), one ring stage per tile
+        TC3_TIMED(0, mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1));
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * p.a_bytes));
+          tma2_load_4d(smem_base + stage * SM::STAGE_BYTES, &tmA, lbar0 + 8u * stage, 0, 0, h0, img);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        continue;
       }
       int kb = 0, cb = 0, tap_s = 0, tap_r = 0;   // k-block -> (filter row, column, 64-channel block)
       for (int kk = 0; kk < p.num_k_blocks; ++kk) {
@@ -783,6 +825,60 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         TC3_TIMED(1, mbar_wait(tmem_empty_bar(ab), (uint32_t)(((it >> 1) & 1) ^ 1), p.err_flag, 5));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BLOCK_N);
+        if (BRES && !HAS_RES && p.im2col == 4) {
+          // nine taps out of one resident patch: tap (dy, dx) is the same 128-row operand started (dy * Wp + dx) pixels
+          // = that many 128 B swizzle rows further on.  The tensor core derives the swizzle phase from the absolute
+          // shared-memory address, like the copy engine that wrote the patch, so a start that is not a multiple of 8 rows
+          // needs nothing else: the descriptor's base-offset field stays 0 (measured: setting it to (address >> 7) & 7
+          // breaks parity, profiles/r02_pytest_halo_base_offset.log)
+          const int st4 = 2 * (it & 3);
+          TC3_TIMED(0, mbar_wait(full_bar(st4), (uint32_t)((it >> 2) & 1), p.err_flag, 2));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t patch = smem_base + st4 * SM::STAGE_BYTES;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - 3 * dy;
+              const uint32_t a_addr = patch + (uint32_t)(dy * p.halo_wp + dx) * 128u;
+              const uint64_t adesc = make_smem_desc_sw128(a_addr);
+              const uint64_t bdesc = make_smem_desc_sw128(smem_base + SM::BRES_OFFSET + tap * SM::BH_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+                umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | k) != 0);
+            }
+            umma2_commit_both(empty_bar(st4));
+            umma2_commit_both(tmem_full_bar(ab));
+          }
+          __syncwarp();
+          continue;
+        }
+        if (BRES && !HAS_RES && p.im2col == 5) {
+          // stem on raw input rows: output pixel q of filter row r reads 32 elements (8 taps x 4 channels) starting at
+          // pixel 2q of input row 2p + r, i.e. 16 q bytes into that row - an unswizzled K-major operand whose rows
+          // OVERLAP (row pitch 16 B, K chunk pitch 16 B).  Each input byte crosses L2 -> SM once per output row instead
+          // of once per tap: 12.9 KB per tile instead of 56 KB of 64-byte rows.
+          TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
+            const uint32_t lbo = p.halo_swap ? 128u : 16u, sbo = p.halo_swap ? 16u : 128u;
+#pragma unroll 1
+            for (int r = 0; r < 7; ++r) {
+              const uint32_t b_addr = smem_base + SM::BRES_OFFSET + (r >> 1) * SM::BH_BYTES + (r & 1) * (SM::BH_BYTES / 2);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adesc = make_smem_desc_nosw(a_addr + (uint32_t)(r * p.halo_wp) + ks * 32, lbo, sbo);
+                const uint64_t bdesc = make_smem_desc_sw64(b_addr + ks * 32);
+                umma2_bf16(d_tmem, adesc, bdesc, idesc, (r | ks) != 0);
+              }
+            }
+            umma2_commit_both(empty_bar(stage));
+            umma2_commit_both(tmem_full_bar(ab));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          continue;
+        }
         for (int kk = 0; kk < p.num_k_blocks; ++kk) {
           const int kb = kk;
           TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
@@ -841,6 +937,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int tile = SM::SPLIT_COLS ? pair : pair + g * npairs;
     // With ~225 KB of the SM carved out as shared memory there is no L1 to speak of: the tile's bias slice is fetched
     // one tile ahead into a register, parked in smem and read back as broadcast LDS.128.
+    // halo mode: TMEM lane i is raster position i of the padded-width tile; its dense output row (junk columns dropped)
+    const bool halo = BRES && !HAS_RES && !SPLIT && p.im2col == 4;
+    bool halo_valid = false;
+    uint32_t halo_base = 0, halo_sw = 0;
+    if (halo) {
+      const int i = quarter * 32 + lane;
+      const int y = i / p.halo_wp, x = i - y * p.halo_wp;
+      halo_valid = y < p.halo_r && x < p.Q;
+      const int ip = y * p.Q + x;
+      halo_base = box_addr(g) + (uint32_t)ip * 128u;
+      halo_sw = (uint32_t)(ip & 7);
+    }
     float bias_pre = 0.f;
     if (has_bias && wt < SM::CW && tile < total_tiles) bias_pre = __ldg(p.bias + (tile % p.n_tiles) * BLOCK_N + colbase + wt);
     if (dbg_on) t_loop0 = clock64();
@@ -967,6 +1075,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           o[c * 4 + 0] = max_bf16x2(cvt_bf16x2(a0), relu_floor); o[c * 4 + 1] = max_bf16x2(cvt_bf16x2(a1), relu_floor);
           o[c * 4 + 2] = max_bf16x2(cvt_bf16x2(a2), relu_floor); o[c * 4 + 3] = max_bf16x2(cvt_bf16x2(a3), relu_floor);
+        }
+        if (halo) {
+          // the warpgroup's four slabs are one 128-row staging box: rows land compacted at their dense index and ONE
+          // store of tile_rows rows leaves per tile (issued by the warpgroup's first lane, which also owns the drain)
+          if (quarter == 0 && lane == 0) TC3_TIMED(2, bulk_wait_read<0>());
+          TC3_TIMED(3, named_bar_sync(1 + g, 128));
+          if (halo_valid) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              sts_v4(halo_base + ((((uint32_t)c) ^ halo_sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
+          }
+          fence_async_smem();
+          TC3_TIMED(3, named_bar_sync(1 + g, 128));
+          if (quarter == 0 && lane == 0) {
+            tma_store_2d(&tmOutTail, box_addr(g), p.out_coff + n0, m0);
+            bulk_commit();
+          }
+          continue;
         }
         if (!HAS_RES) {              // private slab: the previous store of this warp must have read it
           if (lane == 0) TC3_TIMED(2, bulk_wait_read<0>());
@@ -1461,6 +1587,7 @@ struct TcConvPlan {
   int im2col;
   int tile_rows;
   int num_k_blocks, cblocks;
+  int halo_wp, halo_r, halo_tpi;   // im2col == 4
   unsigned int* err_flag;
 };
 
@@ -1506,6 +1633,23 @@ bool tc_conv_is_stem4(const ConvParams& p) {
          p.out_cstride % 8 == 0 && p.out_coff % 8 == 0 && p.pre_scale == nullptr && p.res == nullptr &&
          p.w_alt != nullptr && (p.Win + 2 * p.in_halo) % 2 == 0 && (p.Win + 2 * p.in_halo) >= 2 * (p.Q - 1) + 8 &&
          (p.Hin + 2 * p.in_halo) >= 2 * (p.P - 1) + 8;
+}
+
+// 3x3 stride-1 pad-1 convolution, 64 -> 64 channels, on the CTA-pair kernel with resident weights: the im2col path reads
+// every input pixel nine times from L2 (16 KB per K block per SM against a ~43 B/clk/SM L2 port: 385 cycles per K block
+// for 128 cycles of MMA), this one loads each tile's input patch once.  Whole image rows per tile, in the raster of the
+// padded width; the junk columns cost 2 / (W + 2) of the MMA work.
+bool tc_conv_is_halo3x3(const ConvParams& p) {
+  static const bool off = getenv("NIB_TC_NO_HALO") != nullptr;
+  if (off || p.split) return false;
+  if (!(p.R == 3 && p.S == 3 && p.stride == 1 && p.pad == 1 && p.Cin == 64 && p.Cout == 64)) return false;
+  if (p.res != nullptr || p.pre_scale != nullptr || p.in_halo != 0 || p.out_halo != 0) return false;
+  if (p.in_cstride % 8 != 0 || p.in_coff % 8 != 0 || p.out_cstride % 8 != 0 || p.out_coff % 8 != 0) return false;
+  if (p.P != p.Hin || p.Q != p.Win) return false;
+  const int Wp = p.Win + 2;
+  if (Wp > 63) return false;                    // the last tap's 128 rows must stay inside the 32 KB patch buffer
+  const int R = TC_BLOCK_M / Wp;
+  return R >= 1 && p.Hin % R == 0 && (R + 2) * Wp <= 256;
 }
 
 bool tc_conv_supported(const ConvParams& p) {
@@ -1587,7 +1731,31 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
     plan->num_k_blocks = 4;
     plan->tile_rows = p.Q;
     const int Hp = p.Hin + 6, Wp = p.Win + 6;
+    // raw-row mode (5): the padded row (Wp pixels x 4 channels) as inner x outer with a TMA-legal inner extent
+    int inner = 0;
     {
+      static const bool off = getenv("NIB_TC_NO_HALO") != nullptr;
+      const int row_el = Wp * 4;
+      if (!off && 6 * Wp * 8 + 16 * 127 + 64 <= 16384)
+        for (int c = 256; c >= 8; c -= 8)
+          if (row_el % c == 0 && row_el / c <= 256) { inner = c; break; }
+    }
+    if (inner > 0) {
+      plan->im2col = 5;
+      plan->halo_wp = Wp * 8;
+      cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)(Wp * 4 / inner), (cuuint64_t)Hp, (cuuint64_t)max_batch};
+      cuuint64_t strides[3] = {(cuuint64_t)inner * 2, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
+      cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)(Wp * 4 / inner), 7, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = g_encodeTiled(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides,
+                                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (stem, raw rows) failed (%d)", (int)r);
+        delete plan;
+        return NIB_ECUDA;
+      }
+    } else {
       // one filter row of one output row: {window element (8 pixels x 4 ch), output pixel q (+2 pixels), input row, image}
       cuuint64_t dims[4] = {32, (cuuint64_t)p.Q, (cuuint64_t)Hp, (cuuint64_t)max_batch};
       cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)Hp * Wp * 8};
@@ -1644,6 +1812,41 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
       return NIB_ECUDA;
     }
     rc = finish_plan(plan, p, max_batch, p.w_alt, 7 * 64);
+    if (rc != NIB_OK) { delete plan; return rc; }
+    *out = plan;
+    return NIB_OK;
+  }
+  if (tc_conv_is_halo3x3(p)) {
+    const int Wp = p.Win + 2, R = TC_BLOCK_M / Wp;
+    plan->im2col = 4;
+    plan->cblocks = 1;
+    plan->num_k_blocks = 9;
+    plan->tile_rows = R * p.Win;
+    plan->halo_wp = Wp; plan->halo_r = R; plan->halo_tpi = p.Hin / R;
+    rc = encode_2d_bf16(&plan->tmB, p.w, 9 * 64, (uint64_t)p.Cout, 9 * 64 * 2, TC_BLOCK_K, plan->block_n);
+    if (rc != NIB_OK) { delete plan; return rc; }
+    {
+      // the dense NHWC input as {channel, column, row, image}; the box is the whole patch of one tile
+      cuuint64_t dims[4] = {(cuuint64_t)p.in_cstride, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)max_batch};
+      cuuint64_t strides[3] = {(cuuint64_t)p.in_cstride * 2, (cuuint64_t)p.Win * p.in_cstride * 2,
+                               (cuuint64_t)p.Hin * p.Win * p.in_cstride * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)Wp, (cuuint32_t)(R + 2), 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = g_encodeTiled(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides,
+                                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3x3 halo patch) failed (%d)", (int)r);
+        delete plan;
+        return NIB_ECUDA;
+      }
+    }
+    rc = finish_plan(plan, p, max_batch, p.w, 9 * 64);
+    if (rc != NIB_OK) { delete plan; return rc; }
+    // the kernel's "tail" slot carries the whole-tile output box in this mode
+    const uint64_t rows = (uint64_t)max_batch * p.P * p.Q;
+    rc = encode_2d_bf16(&plan->tmOutTail, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
+                        (uint32_t)plan->tile_rows);
     if (rc != NIB_OK) { delete plan; return rc; }
     *out = plan;
     return NIB_OK;
@@ -2001,6 +2204,16 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.lo_off_out = p.out_lo_off;
   kp.lo_off_res = p.res_lo_off;
   kp.dyn_n = plan->split ? p.dyn_n : nullptr;
+  if (plan->im2col == 4) {
+    kp.halo_wp = plan->halo_wp; kp.halo_r = plan->halo_r; kp.halo_tpi = plan->halo_tpi;
+    kp.a_bytes = (plan->halo_r + 2) * plan->halo_wp * 128;
+  }
+  if (plan->im2col == 5) {
+    static const bool swap = getenv("NIB_TC_STEM_SWAP") != nullptr;
+    kp.halo_wp = plan->halo_wp;          // bytes of one padded input row
+    kp.halo_swap = swap ? 1 : 0;
+    kp.a_bytes = 7 * plan->halo_wp;
+  }
   const int tiles = kp.m_tiles * kp.n_tiles;
   static const bool dbg = getenv("NIB_TC_DBG") != nullptr;
   if (dbg && plan->v3) return tc_launch_debug(plan, kp, p, tiles, st);

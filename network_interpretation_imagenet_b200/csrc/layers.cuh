@@ -44,6 +44,9 @@ int launch_conv_simt(const ConvParams& p, bool bf16, cudaStream_t st);
 bool conv_x3_supported(const ConvParams& p);
 int launch_conv_x3(const ConvParams& p, const void* w_hi, const void* w_lo, cudaStream_t st);
 int launch_pool(const PoolParams& p, bool bf16, cudaStream_t st);
+bool fc_x2_supported(int Cin, int feat_stride);
+int launch_fc_x2(const void* feat, int feat_stride, const void* w_hi, const void* w_lo, const float* b, int N, int Cin,
+                 int Cout, float* logits, const int* dyn_n, cudaStream_t st);
 int launch_fc(const void* feat, int feat_stride, bool bf16, const float* w, const float* b, int N, int Cin,
               int Cout, float* logits, const int* dyn_n, cudaStream_t st);
 int launch_bnrelu_pack(const void* x, int in_cstride, int in_coff, int Cin, int Cpad, const float* scale,

@@ -364,6 +364,21 @@ int nib_net_add_fc(nib_net* net, int in_buf, int Cin, int Cout, const float* h_w
   op.d_w = w;
   rc = upload_floats(h_bias, Cout, &op.d_bias);
   if (rc != NIB_OK) return rc;
+  if (bi.kind == BUF_BF16 && fc_x2_supported(Cin, bi.C)) {   // bf16 features: tensor-core fc on W = hi + lo (conv_x3.cu)
+    const size_t nel = (size_t)Cin * Cout;
+    std::vector<uint16_t> hi(nel), lo(nel);
+    for (size_t i = 0; i < nel; ++i) {
+      hi[i] = f32_to_bf16_rn(h_weight[i]);
+      uint32_t u = (uint32_t)hi[i] << 16;
+      float hf;
+      memcpy(&hf, &u, 4);
+      lo[i] = f32_to_bf16_rn(h_weight[i] - hf);
+    }
+    NIB_CUDA(cudaMalloc(&op.d_w_hi, nel * 2 + 256));
+    NIB_CUDA(cudaMalloc(&op.d_w_lo, nel * 2 + 256));
+    NIB_CUDA(cudaMemcpy(op.d_w_hi, hi.data(), nel * 2, cudaMemcpyHostToDevice));
+    NIB_CUDA(cudaMemcpy(op.d_w_lo, lo.data(), nel * 2, cudaMemcpyHostToDevice));
+  }
   net->ops.push_back(op);
   net->num_classes = Cout;
   return NIB_OK;
@@ -542,8 +557,11 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
       if (rc != NIB_OK) return rc;
     } else {
       const NetBuffer& bi = net->bufs[op.fc_in];
-      int rc = launch_fc(bi.ptr, bi.C, bi.kind == BUF_BF16, (const float*)op.d_w, op.d_bias, N, op.fc_cin, op.fc_cout,
-                         d_logits, net->dyn_n, st);
+      static const bool fc_simt = getenv("NIB_FC_SIMT") != nullptr;   // A/B: the CUDA-core SGEMM
+      int rc = (op.d_w_hi && !fc_simt)
+                   ? launch_fc_x2(bi.ptr, bi.C, op.d_w_hi, op.d_w_lo, op.d_bias, N, op.fc_cin, op.fc_cout, d_logits, net->dyn_n, st)
+                   : launch_fc(bi.ptr, bi.C, bi.kind == BUF_BF16, (const float*)op.d_w, op.d_bias, N, op.fc_cin, op.fc_cout,
+                               d_logits, net->dyn_n, st);
       net->launches++;
       if (rc != NIB_OK) return rc;
     }

@@ -103,10 +103,15 @@ CONV_CASES = [
     (256, 512, 1, 2, 0, 28, 28, False, False),
     (128, 32, 3, 1, 1, 7, 7, False, False),
     (512, 512, 3, 1, 1, 7, 7, True, True),
+    # 3x3 64 -> 64 on the resident input patch (conv_tc.cu im2col mode 4): 2 / 4 / 8 image rows per tile; N = 5 images
+    # makes the tile count odd, so one CTA of the last pair runs past the batch
+    (64, 64, 3, 1, 1, 56, 56, True, False),
+    (64, 64, 3, 1, 1, 32, 30, False, False),
+    (64, 64, 3, 1, 1, 16, 14, True, False),
 ]
 
 
-@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "cin%d_cout%d_k%d_s%d_h%d" % (c[0], c[1], c[2], c[3], c[5]))
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "cin%d_cout%d_k%d_s%d_h%d_w%d" % (c[0], c[1], c[2], c[3], c[5], c[6]))
 def test_conv_tcgen05_vs_torch(nib, case):
     Cin, Cout, k, stride, pad, H, W, relu, residual = case
     got, ref, net = _one_conv_net(nib, "bf16", Cin, Cout, k, stride, pad, H, W, relu, residual, N=5, seed=sum(case[:7]))
