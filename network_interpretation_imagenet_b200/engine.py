@@ -34,9 +34,11 @@ from .scoring import score
 # literally (band 2e-2) would send 99.6 % of the masks of this near-tied random-init network to fp32.  Trained networks
 # have top-2 margins far outside any of these bands and the policy costs them one empty launch sequence (~0.6 ms).
 DEFAULT_TIE_BAND = 4.5e-3
-DEFAULT_TIE_CAPACITY = 640      # rows of the re-score buffer per window of masks
-DEFAULT_TIE_WINDOW = 4096       # masks scored per tie-policy pass (capacity = 15.6 % of a window: the seeded DenseNet-121,
-                                # the most tied of the networks here, has 13 % of its masks inside the band)
+DEFAULT_TIE_CAPACITY = 1024     # rows of the re-score buffer per window of masks
+DEFAULT_TIE_WINDOW = 4096       # masks scored per tie-policy pass (capacity = 25 % of a window: the seeded DenseNet-121,
+                                # the most tied of the networks here, has 13 % of its masks inside the band on average and
+                                # overflowed a 640-row buffer in 24 of 4096 masks per window, profiles/r02_bench_final_n8_
+                                # densenet_config5.json; the pass costs what its live rows cost, not what the buffer holds)
 
 
 def shard_range(N: int, rank: int, world: int) -> tuple[int, int, int]:
