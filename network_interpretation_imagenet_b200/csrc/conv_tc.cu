@@ -71,6 +71,8 @@ struct TcKernelParams {
   // width halo_wp = Q + 2; the (halo_r + 2) x halo_wp input patch is loaded once and all nine taps read it at shifted
   // start addresses
   int halo_wp, halo_r, halo_tpi;   // padded width, image rows per tile, tiles per image
+  int halo_cb, halo_n;             // 64-channel blocks of Cin (1 | 2: one 32 KB patch block each) and the MMA's N (64 | 32:
+                                   // DenseNet's 128 -> 32 growth convs; the weights stay resident either way, 36 KB per CTA)
   int halo_swap;                   // im2col == 5 diagnostics: swap the LBO / SBO roles of the unswizzled descriptor
 };
 
@@ -683,7 +685,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int it = 0;
     const uint32_t lbar0 = mapa_shared(full_bar(0), 0);   // leader CTA's full barriers
     const uint32_t tx_bytes = (uint32_t)(2 * (p.a_bytes + (BRES ? 0 : SM::BH_BYTES)));
-    const int b_row0 = (int)rank * (BLOCK_N / 2);
+    const int b_row0 = (int)rank * ((BRES && p.im2col == 4 ? p.halo_n : BLOCK_N) / 2);
     // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
     // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
     // busy epilogue never stalls the operand ring
@@ -712,9 +714,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (BRES) {   // both CTAs fetch their half of every K block of the weights once
       if (elect_one()) {
         const uint32_t lb = mapa_shared(bres_full_bar, 0);
-        if (rank == 0) mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(2 * p.num_k_blocks * SM::BH_BYTES));
+        const uint32_t bhb = p.im2col == 4 ? (uint32_t)(p.halo_n * 64) : (uint32_t)SM::BH_BYTES;   // halo_n / 2 rows x 128 B
+        if (rank == 0) mbar_arrive_expect_tx(bres_full_bar, (uint32_t)(2 * p.num_k_blocks) * bhb);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          const uint32_t dst = smem_base + SM::BRES_OFFSET + kb * SM::BH_BYTES;
+          const uint32_t dst = smem_base + SM::BRES_OFFSET + kb * bhb;
           if (p.im2col == 3 || p.im2col == 5) {   // 64B-swizzled: the K block is two 32-element atoms
             tma2_load_2d(dst, &tmB, lb, kb * TC_BLOCK_K, b_row0);
             tma2_load_2d(dst + SM::BH_BYTES / 2, &tmB, lb, kb * TC_BLOCK_K + 32, b_row0);
@@ -746,13 +749,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (BRES && !HAS_RES && p.im2col == 4) {
         // halo patch: ONE 4D tiled load per tile (rows y0-1 .. y0+halo_r, columns -1 .. Q; out-of-range coordinates are
         // zero-filled = the convolution's padding) into one of four 32 KB buffers (ring stages 0, 2, 4, 6)
-        const int st4 = 2 * (it & 3);
-        TC3_TIMED(0, mbar_wait(empty_bar(st4), (uint32_t)(((it >> 2) & 1) ^ 1), p.err_flag, 1));
+        // (two 32 KB blocks per buffer and two buffers when Cin = 128)
+        const int npb = 4 / p.halo_cb, pbuf = it % npb;
+        const int st4 = 2 * p.halo_cb * pbuf;
+        TC3_TIMED(0, mbar_wait(empty_bar(st4), (uint32_t)(((it / npb) & 1) ^ 1), p.err_flag, 1));
         if (elect_one()) {
           const int im = m_tile / p.halo_tpi;
           const int y0 = (m_tile - im * p.halo_tpi) * p.halo_r;
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(st4), (uint32_t)(2 * p.a_bytes));
-          tma2_load_4d(smem_base + st4 * SM::STAGE_BYTES, &tmA, lbar0 + 8u * st4, p.in_coff, -1, y0 - 1, im);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(st4), (uint32_t)(2 * p.halo_cb * p.a_bytes));
+          for (int c = 0; c < p.halo_cb; ++c)
+            tma2_load_4d(smem_base + (st4 + 2 * c) * SM::STAGE_BYTES, &tmA, lbar0 + 8u * st4, p.in_coff + 64 * c, -1, y0 - 1, im);
         }
         __syncwarp();
         continue;
@@ -831,20 +837,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // shared-memory address, like the copy engine that wrote the patch, so a start that is not a multiple of 8 rows
           // needs nothing else: the descriptor's base-offset field stays 0 (measured: setting it to (address >> 7) & 7
           // breaks parity, profiles/r02_pytest_halo_base_offset.log)
-          const int st4 = 2 * (it & 3);
-          TC3_TIMED(0, mbar_wait(full_bar(st4), (uint32_t)((it >> 2) & 1), p.err_flag, 2));
+          const int npb = 4 / p.halo_cb, pbuf = it % npb;
+          const int st4 = 2 * p.halo_cb * pbuf;
+          TC3_TIMED(0, mbar_wait(full_bar(st4), (uint32_t)((it / npb) & 1), p.err_flag, 2));
           tc_fence_after();
           if (elect_one()) {
             const uint32_t patch = smem_base + st4 * SM::STAGE_BYTES;
+            const uint32_t bhb = (uint32_t)(p.halo_n * 64);
+            const uint32_t idesc_h = p.halo_n == 32 ? make_idesc_bf16_pair<32>() : idesc;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int kb = 0; kb < 9 * p.halo_cb; ++kb) {      // K order of the KRSC weights: tap major, channel block minor
+              const int tap = p.halo_cb == 2 ? (kb >> 1) : kb, c = p.halo_cb == 2 ? (kb & 1) : 0;
               const int dy = tap / 3, dx = tap - 3 * dy;
-              const uint32_t a_addr = patch + (uint32_t)(dy * p.halo_wp + dx) * 128u;
+              const uint32_t a_addr = patch + (uint32_t)(2 * c) * SM::STAGE_BYTES + (uint32_t)(dy * p.halo_wp + dx) * 128u;
               const uint64_t adesc = make_smem_desc_sw128(a_addr);
-              const uint64_t bdesc = make_smem_desc_sw128(smem_base + SM::BRES_OFFSET + tap * SM::BH_BYTES);
+              const uint64_t bdesc = make_smem_desc_sw128(smem_base + SM::BRES_OFFSET + (uint32_t)kb * bhb);
 #pragma unroll
               for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-                umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | k) != 0);
+                umma2_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_h, (kb | k) != 0);
             }
             umma2_commit_both(empty_bar(st4));
             umma2_commit_both(tmem_full_bar(ab));
@@ -946,11 +956,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int y = i / p.halo_wp, x = i - y * p.halo_wp;
       halo_valid = y < p.halo_r && x < p.Q;
       const int ip = y * p.Q + x;
-      halo_base = box_addr(g) + (uint32_t)ip * 128u;
-      halo_sw = (uint32_t)(ip & 7);
+      if (p.halo_n == 32) {   // 32 channels = 64 B rows under the 64B swizzle (16-byte chunk ^= address bits 7..8)
+        halo_base = box_addr(g) + (uint32_t)ip * 64u;
+        halo_sw = (uint32_t)((ip >> 1) & 3);
+      } else {
+        halo_base = box_addr(g) + (uint32_t)ip * 128u;
+        halo_sw = (uint32_t)(ip & 7);
+      }
     }
     float bias_pre = 0.f;
-    if (has_bias && wt < SM::CW && tile < total_tiles) bias_pre = __ldg(p.bias + (tile % p.n_tiles) * BLOCK_N + colbase + wt);
+    const int bias_cols = (BRES && p.im2col == 4) ? p.halo_n : SM::CW;   // the resident-patch mode may have only 32 outputs
+    if (has_bias && wt < bias_cols && tile < total_tiles) bias_pre = __ldg(p.bias + (tile % p.n_tiles) * BLOCK_N + colbase + wt);
     if (dbg_on) t_loop0 = clock64();
     for (; tile < total_tiles; tile += step, it += (SM::SPLIT_COLS ? 1 : 2), ++lt) {
       const int n_tile = tile % p.n_tiles;
@@ -966,7 +982,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (wt < SM::CW) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * wt), "f"(bias_pre) : "memory");
         TC3_TIMED(3, named_bar_sync(1 + g, 128));
         const int nt = tile + step;
-        if (wt < SM::CW && nt < total_tiles) bias_pre = __ldg(p.bias + (nt % p.n_tiles) * BLOCK_N + colbase + wt);
+        if (wt < bias_cols && nt < total_tiles) bias_pre = __ldg(p.bias + (nt % p.n_tiles) * BLOCK_N + colbase + wt);
       }
       const int set = it % SM::RSETS;
       const uint32_t rpar = (uint32_t)((it / SM::RSETS) & 1);
@@ -1084,7 +1100,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (halo_valid) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              sts_v4(halo_base + ((((uint32_t)c) ^ halo_sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
+              if (c < 4 || p.halo_n == 64)
+                sts_v4(halo_base + ((((uint32_t)c) ^ halo_sw) << 4), make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]));
           }
           fence_async_smem();
           TC3_TIMED(3, named_bar_sync(1 + g, 128));
@@ -1587,7 +1604,7 @@ struct TcConvPlan {
   int im2col;
   int tile_rows;
   int num_k_blocks, cblocks;
-  int halo_wp, halo_r, halo_tpi;   // im2col == 4
+  int halo_wp, halo_r, halo_tpi, halo_cb, halo_n;   // im2col == 4
   unsigned int* err_flag;
 };
 
@@ -1642,7 +1659,9 @@ bool tc_conv_is_stem4(const ConvParams& p) {
 bool tc_conv_is_halo3x3(const ConvParams& p) {
   static const bool off = getenv("NIB_TC_NO_HALO") != nullptr;
   if (off || p.split) return false;
-  if (!(p.R == 3 && p.S == 3 && p.stride == 1 && p.pad == 1 && p.Cin == 64 && p.Cout == 64)) return false;
+  if (!(p.R == 3 && p.S == 3 && p.stride == 1 && p.pad == 1)) return false;
+  // resident weights: 9 x (Cin / 64) K blocks of Cout / 2 rows must fit the 36 KB the 64-channel instance reserves
+  if (!((p.Cin == 64 && (p.Cout == 64 || p.Cout == 32)) || (p.Cin == 128 && p.Cout == 32))) return false;
   if (p.res != nullptr || p.pre_scale != nullptr || p.in_halo != 0 || p.out_halo != 0) return false;
   if (p.in_cstride % 8 != 0 || p.in_coff % 8 != 0 || p.out_cstride % 8 != 0 || p.out_coff % 8 != 0) return false;
   if (p.P != p.Hin || p.Q != p.Win) return false;
@@ -1819,11 +1838,14 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
   if (tc_conv_is_halo3x3(p)) {
     const int Wp = p.Win + 2, R = TC_BLOCK_M / Wp;
     plan->im2col = 4;
-    plan->cblocks = 1;
-    plan->num_k_blocks = 9;
+    plan->cblocks = p.Cin / 64;
+    plan->num_k_blocks = 9 * plan->cblocks;
     plan->tile_rows = R * p.Win;
     plan->halo_wp = Wp; plan->halo_r = R; plan->halo_tpi = p.Hin / R;
-    rc = encode_2d_bf16(&plan->tmB, p.w, 9 * 64, (uint64_t)p.Cout, 9 * 64 * 2, TC_BLOCK_K, plan->block_n);
+    plan->halo_cb = plan->cblocks; plan->halo_n = p.Cout;
+    plan->block_n = 64;                               // the kernel instance; the MMA's N is halo_n
+    const int Kh = 9 * p.Cin;
+    rc = encode_2d_bf16(&plan->tmB, p.w, (uint64_t)Kh, (uint64_t)p.Cout, (uint64_t)Kh * 2, TC_BLOCK_K, (uint32_t)p.Cout);
     if (rc != NIB_OK) { delete plan; return rc; }
     {
       // the dense NHWC input as {channel, column, row, image}; the box is the whole patch of one tile
@@ -1841,13 +1863,27 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
         return NIB_ECUDA;
       }
     }
-    rc = finish_plan(plan, p, max_batch, p.w, 9 * 64);
+    // each CTA of the pair holds Cout / 2 weight rows per K block; the kernel's "tail" slot carries the whole-tile output
+    // box (Cout channels: 64 B rows under the 64B swizzle when Cout = 32); the other output / residual maps are unused
+    rc = encode_2d_bf16(&plan->tmBh, p.w, (uint64_t)Kh, (uint64_t)p.Cout, (uint64_t)Kh * 2, TC_BLOCK_K, (uint32_t)(p.Cout / 2));
     if (rc != NIB_OK) { delete plan; return rc; }
-    // the kernel's "tail" slot carries the whole-tile output box in this mode
-    const uint64_t rows = (uint64_t)max_batch * p.P * p.Q;
-    rc = encode_2d_bf16(&plan->tmOutTail, p.out, (uint64_t)p.out_cstride, rows, (uint64_t)p.out_cstride * 2, 64,
-                        (uint32_t)plan->tile_rows);
-    if (rc != NIB_OK) { delete plan; return rc; }
+    {
+      const uint64_t rows = (uint64_t)max_batch * p.P * p.Q;
+      cuuint64_t dims[2] = {(cuuint64_t)p.out_cstride, rows};
+      cuuint64_t strides[1] = {(cuuint64_t)p.out_cstride * 2};
+      cuuint32_t box[2] = {(cuuint32_t)p.Cout, (cuuint32_t)plan->tile_rows};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = g_encodeTiled(&plan->tmOutTail, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out, dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, p.Cout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3x3 halo output box) failed (%d)", (int)r);
+        delete plan;
+        return NIB_ECUDA;
+      }
+    }
+    plan->tmOut = plan->tmOut32 = plan->tmRes = plan->tmOutTail;
+    plan->v3 = 1;
     *out = plan;
     return NIB_OK;
   }
@@ -2103,6 +2139,7 @@ static int tc_dispatch(const TcConvPlan* plan, const TcKernelParams& kp, int til
   if (plan->v3 && !kp.out_f32) {
     // CTA-pair kernel; stage counts fill the 227 KB of each SM (ring + output/residual boxes)
     const bool res = kp.res != nullptr;
+    if (plan->im2col == 4) return launch_tc3<64, 9, false, true>(plan, kp, st);   // resident patch + resident weights
     if (plan->block_n == 256) return res ? launch_tc3<256, 5, true>(plan, kp, st) : launch_tc3<256, 6, false>(plan, kp, st);
     if (plan->block_n == 128) return res ? launch_tc3<128, 6, true>(plan, kp, st) : launch_tc3<128, 8, false>(plan, kp, st);
     if (plan->block_n == 64 && !res && kp.n_tiles == 1 && kp.num_k_blocks <= TC3_BRES_KBLOCKS)
@@ -2205,6 +2242,8 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.lo_off_res = p.res_lo_off;
   kp.dyn_n = plan->split ? p.dyn_n : nullptr;
   if (plan->im2col == 4) {
+    kp.n_tiles = 1;
+    kp.halo_cb = plan->halo_cb; kp.halo_n = plan->halo_n;
     kp.halo_wp = plan->halo_wp; kp.halo_r = plan->halo_r; kp.halo_tpi = plan->halo_tpi;
     kp.a_bytes = (plan->halo_r + 2) * plan->halo_wp * 128;
   }

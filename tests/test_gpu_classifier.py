@@ -108,6 +108,10 @@ CONV_CASES = [
     (64, 64, 3, 1, 1, 56, 56, True, False),
     (64, 64, 3, 1, 1, 32, 30, False, False),
     (64, 64, 3, 1, 1, 16, 14, True, False),
+    # same mode with two channel blocks and 32 outputs (DenseNet growth convs): 64-byte output rows under the 64B swizzle
+    (128, 32, 3, 1, 1, 56, 56, False, False),
+    (128, 32, 3, 1, 1, 28, 28, True, False),
+    (64, 32, 3, 1, 1, 16, 14, True, False),
 ]
 
 
