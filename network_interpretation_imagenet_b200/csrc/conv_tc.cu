@@ -73,6 +73,11 @@ struct TcKernelParams {
   int halo_wp, halo_r, halo_tpi;   // padded width, image rows per tile, tiles per image
   int halo_cb, halo_n;             // 64-channel blocks of Cin (1 | 2: one 32 KB patch block each) and the MMA's N (64 | 32:
                                    // DenseNet's 128 -> 32 growth convs; the weights stay resident either way, 36 KB per CTA)
+  // pre-activation (DenseNet BN-ReLU-conv 1x1): y = relu(x * xf_scale[c] + xf_shift[c]) applied to the A tile in shared
+  // memory by four extra warps per CTA between the TMA load and the MMA (arrays zero-padded to the 64-channel K block:
+  // channels past Cin become exact zeros whatever the concat buffer holds there)
+  const float* xf_scale;
+  const float* xf_shift;
   int halo_swap;                   // im2col == 5 diagnostics: swap the LBO / SBO roles of the unswizzled descriptor
 };
 
@@ -432,6 +437,8 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
 //     place), so a 128 x 256 tile with residual still leaves room for a 5-deep ring;
 //   * the tile order keeps the CTA pairs that share activation rows adjacent in time (n fastest).
 static constexpr int TC3_THREADS = 64 + 256;
+static constexpr int TC3_XF_WARPS = 4;                         // pre-activation mode: warps 10..13 transform the A tiles
+static constexpr int TC3_THREADS_XF = TC3_THREADS + 32 * TC3_XF_WARPS;
 
 // BRES: the layer's whole weight matrix (Cout == BLOCK_N, <= 9 K blocks: the 64-channel layers and the stem) is loaded
 // once per CTA and stays resident; the ring then carries activation tiles only, which halves the TMA instructions
@@ -456,7 +463,8 @@ struct Tc3Smem {
   static constexpr int BOX_OFFSET = BRES_OFFSET + BRES_BYTES;
   static constexpr int BIAS_OFFSET = BOX_OFFSET + NBUF * BOX_BYTES;   // [warpgroup][2][CW] floats: the tile's folded-BN bias
   static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * 2 * CW * 4;
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF + 1;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF + 1 + 2 * STAGES;   // + A-landed (local) and A-transformed
+                                                                                 // (leader) per stage: pre-activation mode
   static constexpr int EMPTY_ARRIVALS = SPLIT_COLS ? 16 : 8;         // epilogue warps (both CTAs) that drain one accumulator
   // dynamic smem is the only shared allocation of the kernel, so it starts 1024-aligned in the CTA window; the kernel
   // checks that (the 128B swizzle needs it) instead of spending 1 KB of slack on it
@@ -587,7 +595,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_pair() {
 }
 
 template <int BLOCK_N, int STAGES, bool HAS_RES, bool BRES, bool SPLIT = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS_XF, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutTail,
                 const __grid_constant__ CUtensorMap tmRes, const TcKernelParams p) {
@@ -606,6 +614,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto res_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
   auto box_free_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + SM::NBUF + b); };
   const uint32_t bres_full_bar = bar_base + 8u * (2 * STAGES + 4 + 2 * SM::NBUF);   // used in the leader CTA
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 5 + 2 * SM::NBUF + s); };            // this CTA's A tile landed
+  auto xf_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 5 + 2 * SM::NBUF + s); };               // leader: both transformed
+  const bool xform = !BRES && !SPLIT && p.xf_scale != nullptr;
   const uint32_t tmem_slot = bar_base + 8u * SM::NUM_BARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   auto box_addr = [&](int buf) { return smem_base + SM::BOX_OFFSET + (uint32_t)buf * SM::BOX_BYTES; };
@@ -658,6 +669,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(box_free_bar(b), 4);   // the four warps that store a box hand it back
     }
     mbar_init(bres_full_bar, 1);
+    for (int s2 = 0; s2 < STAGES; ++s2) {
+      mbar_init(afull_bar(s2), 1);
+      mbar_init(xf_bar(s2), 2 * TC3_XF_WARPS);   // the transform warps of both CTAs
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -684,7 +699,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     int it = 0;
     const uint32_t lbar0 = mapa_shared(full_bar(0), 0);   // leader CTA's full barriers
-    const uint32_t tx_bytes = (uint32_t)(2 * (p.a_bytes + (BRES ? 0 : SM::BH_BYTES)));
+    const uint32_t tx_bytes = (uint32_t)(2 * ((xform ? 0 : p.a_bytes) + (BRES ? 0 : SM::BH_BYTES)));
     const int b_row0 = (int)rank * ((BRES && p.im2col == 4 ? p.halo_n : BLOCK_N) / 2);
     // residual boxes of the previous tile still to be requested: they are issued opportunistically while this
     // tile's operands stream (a box frees up when the epilogue's store of the tile before has drained), so a
@@ -792,6 +807,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // K block kb = filter rows 2kb, 2kb+1: two 64B-swizzled K atoms of [Q rows x 32 elements]
             tma2_load_4d(a_dst, &tmA, lbar, 0, 0, h0 + 2 * kb, img);
             tma2_load_4d(a_dst + SM::A_BYTES / 2, &tmA, lbar, 0, 0, h0 + 2 * kb + 1, img);
+          } else if (xform) {
+            // pre-activation: this CTA's A tile completes on its OWN barrier (its transform warps cannot wait on the leader's)
+            mbar_arrive_expect_tx(afull_bar(stage), (uint32_t)p.a_bytes);
+            tma_load_2d(a_dst, &tmA, afull_bar(stage), c0, m0);
           } else {
             tma2_load_2d(a_dst, &tmA, lbar, c0, m0);
           }
@@ -892,6 +911,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kk = 0; kk < p.num_k_blocks; ++kk) {
           const int kb = kk;
           TC3_TIMED(0, mbar_wait(full_bar(stage), phase, p.err_flag, 2));
+          if (xform) TC3_TIMED(0, mbar_wait(xf_bar(stage), phase, p.err_flag, 8));
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
@@ -922,6 +942,47 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
         d[2] = (unsigned long long)t_acc[0]; d[3] = (unsigned long long)t_acc[1];
         d[9] = (unsigned long long)(clock64() - t_loop0);
+      }
+    }
+  } else if (warp >= 2 + 8) {
+    // ===== pre-activation transform (launched only when p.xf_scale is set): relu(x * scale + shift) in place on every A
+    // tile, between its TMA completion and the MMA.  Thread t owns the 16-byte chunk of logical channels 8 (t % 8) .. +7 in
+    // rows t / 8 + 16 i: its eight scales and shifts live in registers for the whole K block, a warp touches 512
+    // contiguous bytes per access (conflict-free), and the arithmetic is the pack kernel's (fmaf, fmaxf, round to nearest).
+    if (xform) {
+      const int t = (int)threadIdx.x - 32 * (2 + 8);
+      const int cl = t & 7, rb = t >> 3;
+      const uint32_t lead_xf0 = mapa_shared(xf_bar(0), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        for (int kk = 0; kk < p.num_k_blocks; ++kk) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.xf_scale + kk * TC_BLOCK_K + 8 * cl));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.xf_scale + kk * TC_BLOCK_K + 8 * cl + 4));
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.xf_shift + kk * TC_BLOCK_K + 8 * cl));
+          const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.xf_shift + kk * TC_BLOCK_K + 8 * cl + 4));
+          mbar_wait(afull_bar(stage), phase, p.err_flag, 9);
+          const uint32_t a_addr = smem_base + stage * SM::STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rb + 16 * i;
+            const uint32_t addr = a_addr + (uint32_t)r * 128u + ((uint32_t)(cl ^ (r & 7)) << 4);
+            const uint4 raw = lds_v4(addr);
+            const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const float2 a = __bfloat1622float2(v[0]), b = __bfloat1622float2(v[1]), c = __bfloat1622float2(v[2]), d = __bfloat1622float2(v[3]);
+            uint4 o;
+            __nv_bfloat162 q;
+            q = __floats2bfloat162_rn(fmaxf(fmaf(a.x, s0.x, h0.x), 0.f), fmaxf(fmaf(a.y, s0.y, h0.y), 0.f)); o.x = *reinterpret_cast<uint32_t*>(&q);
+            q = __floats2bfloat162_rn(fmaxf(fmaf(b.x, s0.z, h0.z), 0.f), fmaxf(fmaf(b.y, s0.w, h0.w), 0.f)); o.y = *reinterpret_cast<uint32_t*>(&q);
+            q = __floats2bfloat162_rn(fmaxf(fmaf(c.x, s1.x, h1.x), 0.f), fmaxf(fmaf(c.y, s1.y, h1.y), 0.f)); o.z = *reinterpret_cast<uint32_t*>(&q);
+            q = __floats2bfloat162_rn(fmaxf(fmaf(d.x, s1.z, h1.z), 0.f), fmaxf(fmaf(d.y, s1.w, h1.w), 0.f)); o.w = *reinterpret_cast<uint32_t*>(&q);
+            sts_v4(addr, o);
+          }
+          fence_async_smem();     // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(lead_xf0 + 8u * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else {
@@ -1656,6 +1717,13 @@ bool tc_conv_is_stem4(const ConvParams& p) {
 // every input pixel nine times from L2 (16 KB per K block per SM against a ~43 B/clk/SM L2 port: 385 cycles per K block
 // for 128 cycles of MMA), this one loads each tile's input patch once.  Whole image rows per tile, in the raster of the
 // padded width; the junk columns cost 2 / (W + 2) of the MMA work.
+// image rows per tile: the most that fit 128 raster positions of the padded width AND divide the image height (a tile never
+// spans two images: the patch is one box of one image)
+static int halo_rows_per_tile(int H, int Wp) {
+  for (int r = TC_BLOCK_M / Wp; r >= 1; --r)
+    if (H % r == 0) return r;
+  return 0;
+}
 bool tc_conv_is_halo3x3(const ConvParams& p) {
   static const bool off = getenv("NIB_TC_NO_HALO") != nullptr;
   if (off || p.split) return false;
@@ -1667,8 +1735,8 @@ bool tc_conv_is_halo3x3(const ConvParams& p) {
   if (p.P != p.Hin || p.Q != p.Win) return false;
   const int Wp = p.Win + 2;
   if (Wp > 63) return false;                    // the last tap's 128 rows must stay inside the 32 KB patch buffer
-  const int R = TC_BLOCK_M / Wp;
-  return R >= 1 && p.Hin % R == 0 && (R + 2) * Wp <= 256;
+  const int R = halo_rows_per_tile(p.Hin, Wp);
+  return R >= 1 && 2 * R * Wp >= TC_BLOCK_M;    // at least half of the tile's rows are real positions
 }
 
 bool tc_conv_supported(const ConvParams& p) {
@@ -1687,7 +1755,11 @@ bool tc_conv_supported(const ConvParams& p) {
   if (p.Cout % 32 != 0) return false;
   if (p.out_cstride % 8 != 0 || p.out_coff % 8 != 0) return false;
   if (p.in_halo != 0 || p.out_halo != 0) return false;
-  if (p.pre_scale != nullptr) return false;                        // pre-activation needs a register path
+  // pre-activation: only as the in-kernel transform of a 1x1 conv's A tiles on the pair kernel (scale / shift arrays
+  // zero-padded to the K block by the caller, net.cu), never on the im2col / one-CTA paths
+  if (p.pre_scale != nullptr && !(p.pre_padded && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.Cout % 64 == 0 &&
+                                  p.res == nullptr))
+    return false;
   if (p.res != nullptr && (p.res_C != p.Cout || p.res_cstride % 8 != 0 || p.res_coff % 8 != 0)) return false;
   if (p.R != p.S) return false;
   if (p.pad > 127 || p.R > 16) return false;
@@ -1836,7 +1908,7 @@ int tc_conv_plan_create(const ConvParams& p, int max_batch, TcConvPlan** out) {
     return NIB_OK;
   }
   if (tc_conv_is_halo3x3(p)) {
-    const int Wp = p.Win + 2, R = TC_BLOCK_M / Wp;
+    const int Wp = p.Win + 2, R = halo_rows_per_tile(p.Hin, Wp);
     plan->im2col = 4;
     plan->cblocks = p.Cin / 64;
     plan->num_k_blocks = 9 * plan->cblocks;
@@ -2114,7 +2186,7 @@ static int launch_tc3(const TcConvPlan* plan, const TcKernelParams& kp, cudaStre
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(TC3_THREADS);
+  cfg.blockDim = dim3((!BRES && !SPLIT && kp.xf_scale != nullptr) ? TC3_THREADS_XF : TC3_THREADS);
   cfg.dynamicSmemBytes = SM::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -2241,6 +2313,14 @@ int tc_conv_launch(const TcConvPlan* plan, const ConvParams& p, cudaStream_t st)
   kp.lo_off_out = p.out_lo_off;
   kp.lo_off_res = p.res_lo_off;
   kp.dyn_n = plan->split ? p.dyn_n : nullptr;
+  if (p.pre_scale != nullptr) {
+    if (!(p.pre_padded && plan->im2col == 0 && plan->v3 && !plan->split)) {
+      set_error("tc_conv_launch: a pre-activation conv reached a tensor path without the transform role");
+      return NIB_EINVAL;
+    }
+    kp.xf_scale = p.pre_scale;
+    kp.xf_shift = p.pre_shift;
+  }
   if (plan->im2col == 4) {
     kp.n_tiles = 1;
     kp.halo_cb = plan->halo_cb; kp.halo_n = plan->halo_n;

@@ -13,6 +13,8 @@ struct ConvParams {
   void* out;
   const float* pre_scale;  // [Cin] or null (DenseNet pre-activation BN+ReLU on the input)
   const float* pre_shift;
+  int pre_padded;          // 1: both arrays are zero-padded to a multiple of 64 channels and Cin counts the padded channels
+                           // (the pair kernel's in-kernel transform, conv_tc.cu); the weights carry the same zero padding
   int M;                // N * P * Q output pixels
   int Hin, Win, Cin, in_cstride, in_coff, in_halo;
   int P, Q, Cout, out_cstride, out_coff, out_halo;

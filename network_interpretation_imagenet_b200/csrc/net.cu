@@ -34,6 +34,9 @@ struct NetOp {
   float* d_pre_shift;
   void* d_w_pack;     // pre-activation convs in bf16 nets: KRSC weights with Cin zero-padded to a multiple of 64
   int pack_cin;       // that padded Cin (0: no packed tensor-core path for this op)
+  float* d_pre_scale_pad;   // scale / shift zero-padded to pack_cin (the pair kernel's in-kernel transform)
+  float* d_pre_shift_pad;
+  int xform;          // 1: the conv reads the raw channel slice and transforms its A tiles itself (no pack pass)
   void* d_w_hi;       // NIB_PREC_X3: bf16 split of the fp32 KRSC weights, w = hi + lo (conv_x3.cu)
   void* d_w_lo;
   TcConvPlan* plan;
@@ -137,6 +140,8 @@ int nib_net_destroy(nib_net* net) {
     if (o.d_w_lo) cudaFree(o.d_w_lo);
     if (o.d_bias) cudaFree(o.d_bias);
     if (o.d_pre_scale) cudaFree(o.d_pre_scale);
+    if (o.d_pre_scale_pad) cudaFree(o.d_pre_scale_pad);
+    if (o.d_pre_shift_pad) cudaFree(o.d_pre_shift_pad);
     if (o.d_pre_shift) cudaFree(o.d_pre_shift);
     if (o.plan) tc_conv_plan_destroy(o.plan);
     if (o.fplan) tc_fused_plan_destroy(o.fplan);
@@ -317,6 +322,12 @@ int nib_net_add_conv(nib_net* net, const nib_conv_desc* d, const float* h_weight
     if (rc != NIB_OK) return rc;
     rc = upload_floats(h_pre_shift, d->Cin, &op.d_pre_shift);
     if (rc != NIB_OK) return rc;
+    if (op.pack_cin) {
+      std::vector<float> sp(op.pack_cin, 0.f), hp(op.pack_cin, 0.f);
+      for (int c = 0; c < d->Cin; ++c) { sp[c] = h_pre_scale[c]; hp[c] = h_pre_shift[c]; }
+      if ((rc = upload_floats(sp.data(), sp.size(), &op.d_pre_scale_pad)) != NIB_OK) return rc;
+      if ((rc = upload_floats(hp.data(), hp.size(), &op.d_pre_shift_pad)) != NIB_OK) return rc;
+    }
   }
   net->ops.push_back(op);
   return NIB_OK;
@@ -419,6 +430,17 @@ static void fill_conv_params(const nib_net* net, const NetOp& op, int N, ConvPar
   p->dyn_n = net->dyn_n;
 }
 
+// the same conv on the raw channel slice, BN-ReLU applied to the A tiles inside the pair kernel: padded channel count,
+// padded weights, padded scale / shift (channels past Cin come out as exact zeros)
+static void fill_xform_conv_params(const nib_net* net, const NetOp& op, int N, ConvParams* p) {
+  fill_conv_params(net, op, N, p);
+  p->w = op.d_w_pack;
+  p->pre_scale = op.d_pre_scale_pad;
+  p->pre_shift = op.d_pre_shift_pad;
+  p->pre_padded = 1;
+  p->Cin = op.pack_cin;
+}
+
 // the same conv, reading the packed relu(bn(x)) scratch tensor instead of the raw channel slice
 static void fill_packed_conv_params(const nib_net* net, const NetOp& op, int N, ConvParams* p) {
   fill_conv_params(net, op, N, p);
@@ -447,8 +469,14 @@ int nib_net_finalize(nib_net* net) {
   }
   if (net->bf16) {
     // one scratch tensor serves every packed pre-activation conv (ops run one at a time on the stream)
+    static const bool no_xform = getenv("NIB_TC_NO_XFORM") != nullptr;   // A/B: the separate pack pass
     for (auto& op : net->ops) {
       if (op.kind != 0 || op.pack_cin == 0) continue;
+      if (!no_xform && op.d_pre_scale_pad) {
+        ConvParams px;
+        fill_xform_conv_params(net, op, net->max_batch, &px);
+        if (tc_conv_supported(px)) { op.xform = 1; continue; }
+      }
       const NetBuffer& bi = net->bufs[op.cd.in_buf];
       const size_t need = (size_t)net->max_batch * bi.H * bi.W * op.pack_cin * 2;
       if (need > net->pack_scratch_bytes) net->pack_scratch_bytes = need;
@@ -457,6 +485,12 @@ int nib_net_finalize(nib_net* net) {
     for (auto& op : net->ops) {
       if (op.kind != 0) continue;
       ConvParams p;
+      if (op.xform) {
+        fill_xform_conv_params(net, op, net->max_batch, &p);
+        int rc = tc_conv_plan_create(p, net->max_batch, &op.plan);
+        if (rc != NIB_OK) return rc;
+        continue;
+      }
       if (op.pack_cin) {
         fill_packed_conv_params(net, op, net->max_batch, &p);
         if (tc_conv_supported(p)) {
@@ -513,6 +547,10 @@ static int run_ops(nib_net* net, int N, float* d_logits, cudaStream_t st) {
         ConvParams pa;
         fill_conv_params(net, nx, N, &pa);
         rc = tc_fused_launch(op.fplan, p, pa, st);
+        net->tc_launches++;
+      } else if (op.plan && net->use_tc && op.xform) {
+        fill_xform_conv_params(net, op, N, &p);
+        rc = tc_conv_launch(op.plan, p, st);
         net->tc_launches++;
       } else if (op.plan && net->use_tc && op.pack_cin) {
         const NetBuffer& bi = net->bufs[op.cd.in_buf];
