@@ -1736,7 +1736,7 @@ bool tc_conv_is_halo3x3(const ConvParams& p) {
   const int Wp = p.Win + 2;
   if (Wp > 63) return false;                    // the last tap's 128 rows must stay inside the 32 KB patch buffer
   const int R = halo_rows_per_tile(p.Hin, Wp);
-  return R >= 1 && 2 * R * Wp >= TC_BLOCK_M;    // at least half of the tile's rows are real positions
+  return R >= 1 && R * Wp >= 56;                // 7x7 images (one per tile, 63 of 128 rows real) still beat nine im2col boxes
 }
 
 bool tc_conv_supported(const ConvParams& p) {

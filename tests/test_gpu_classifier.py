@@ -113,6 +113,7 @@ CONV_CASES = [
     (128, 32, 3, 1, 1, 28, 28, True, False),
     (64, 32, 3, 1, 1, 16, 14, True, False),
     (128, 32, 3, 1, 1, 14, 14, False, False),     # 7 image rows per tile (8 fit, 7 divides the height)
+    (128, 32, 3, 1, 1, 7, 7, True, False),        # one 7x7 image per tile
 ]
 
 
