@@ -9,6 +9,15 @@
 //     fetches 64 channels of filter tap (r, s) for each, zero-filling the padding.
 // Both land as a 128 x 64 bf16, 128B-swizzled, K-major tile = one tcgen05.mma operand.
 // Weights are KRSC ([Cout][R*S*Cin], BN folded) and arrive through a second tiled map.
+// Round 2 added three ways of NOT fetching one box per tap (the L2 -> SM port, ~43 B/clk/SM, was the bound of the
+// layers concerned), all in conv_tc3_kernel and selected by TcKernelParams::im2col:
+//   * mode 4: 3x3 stride-1 pad-1 convs with 64 -> 64, 64 -> 32 or 128 -> 32 channels read ONE resident input patch per
+//     tile (whole image rows in the raster of the padded width); tap (dy, dx) is the same swizzled operand started
+//     (dy * Wp + dx) rows further on (descriptor base offset 0: the swizzle phase is address-based);
+//   * mode 5: the 7x7 stride-2 stem reads the raw padded input rows through an UNSWIZZLED descriptor whose rows
+//     overlap (row pitch 16 B = the stride-2 window over 8-byte pixels);
+//   * pre-activation 1x1 convs (DenseNet): four extra warps apply relu(x * scale + shift) to every A tile in shared
+//     memory between its TMA completion and the MMA, instead of a separate pack pass.
 //
 // Three kernels live in this file: conv_tc_kernel (one CTA per tile, described next; serves Cout = 32 tiles and the
 // fp32-output GEMM self-test), conv_tc3_kernel (the default: persistent CTA pairs with tcgen05 cta_group::2) and
