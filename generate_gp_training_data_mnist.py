@@ -28,7 +28,9 @@ parser.add_argument("--num_mask_samples", type=int, default=1000)
 parser.add_argument("--image", default=None, help=".npy file holding a 1x28x28 fp32 image in [0,1]")
 parser.add_argument("--target", default=None, type=int)
 parser.add_argument("--mask-seed", default=0, type=int)
-parser.add_argument("--precision", default="fp32", choices=["bf16", "fp32"])
+parser.add_argument("--precision", default="fp32", choices=["bf16", "fp32", "x3"],
+                    help="fp32: CUDA-core parity mode (1e-4); x3: split-bf16 products on the tensor cores, fp32-grade (1e-4); "
+                         "bf16: tcgen05 path (1e-2) with the device-side tie policy")
 parser.add_argument("--checkpoint", default="./saved_checkpoints/mnist/checkpoint.pth.tar")
 parser.add_argument("--no-write", action="store_true")
 
