@@ -99,7 +99,7 @@ def main():
     # warm-up outside the timed regions (like bench.py's warm-up steps): the first call of the tie policy lowers the
     # re-score network, and the first torch.mv / boolean-index / cuBLAS call of a process costs 100-150 ms each
     # (profiles/r02_bo_round_probe.txt: first posterior() 147 ms, first append() 100 ms, 0.44 / 0.70 ms afterwards)
-    eng.score_masks(bits[:512])
+    eng.score_masks(bits[:4096])
     from network_interpretation_imagenet_b200 import gp as _gpmod
     _w = _gpmod.ActiveMaskGP(bits[n:n + 256], alpha=1e-5, length_scale=3.0, normalize_y=True, capacity=4).fit(bits[:256], np.linspace(0.1, 0.9, 256))
     _w.posterior(); _w.append(0, 0.5); _w.posterior()
